@@ -1,0 +1,10 @@
+"""B200-native (sm_100a) implementation of the data-parallel hot path of
+neuronphysics/active-inference-diffusion: reverse-diffusion sampling of the latent score
+network, the score-matching/ELBO loss that trains it and EFE scoring of candidates, behind the
+reference's own Python call surface.  See DESIGN.md."""
+from .configs import ActiveInferenceConfig, BeliefDynamicsConfig, DiffusionConfig
+from .diffusion import LatentDiffusionProcess
+from .score_network import LatentScoreNetwork
+
+__all__ = ["ActiveInferenceConfig", "BeliefDynamicsConfig", "DiffusionConfig",
+           "LatentDiffusionProcess", "LatentScoreNetwork"]

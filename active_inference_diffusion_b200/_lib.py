@@ -1,0 +1,149 @@
+"""ctypes binding of libaid_sm100.so (C ABI declared in include/aid_b200.h).
+
+There is no CPU fallback: `lib()` raises if the shared library is missing, and every compute
+wrapper raises if the tensors are not CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaid_sm100.so")
+
+
+class AidScoreDims(ctypes.Structure):
+    _fields_ = [("latent_dim", c_int32), ("obs_dim", c_int32), ("hidden_dim", c_int32),
+                ("time_embed_dim", c_int32), ("num_blocks", c_int32)]
+
+
+# mirrors enum AidScoreParam / AidScoreBlockParam in include/aid_b200.h
+SCORE_PARAM_KEYS = [
+    "time_scale", "output_multiplier", "time_embed.0.freq_scale",
+    "time_embed.1.weight", "time_embed.1.bias", "time_embed.3.weight", "time_embed.3.bias",
+    "obs_encoder.0.weight", "obs_encoder.0.bias", "obs_encoder.1.weight", "obs_encoder.1.bias",
+    "obs_encoder.4.weight", "obs_encoder.4.bias", "obs_encoder.5.weight", "obs_encoder.5.bias",
+    "obs_encoder.7.weight", "obs_encoder.7.bias", "obs_encoder.8.weight", "obs_encoder.8.bias",
+    "continuous_time_embed.0.weight", "continuous_time_embed.0.bias",
+    "continuous_time_embed.2.weight", "continuous_time_embed.2.bias",
+    "continuous_time_embed.4.weight", "continuous_time_embed.4.bias",
+    "latent_proj.weight", "latent_proj.bias",
+    "norm_final.adaLN_modulation.1.weight", "norm_final.adaLN_modulation.1.bias",
+    "output_proj.0.weight", "output_proj.0.bias", "output_proj.2.weight",
+]
+SCORE_BLOCK_KEYS = [
+    "norm1.adaLN_modulation.1.weight", "norm1.adaLN_modulation.1.bias",
+    "norm2.adaLN_modulation.1.weight", "norm2.adaLN_modulation.1.bias",
+    "attention.in_proj_weight", "attention.in_proj_bias",
+    "attention.out_proj.weight", "attention.out_proj.bias",
+    "mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias",
+]
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def _declare(l: ctypes.CDLL) -> None:
+    P = POINTER
+    l.aid_abi_version.restype = c_int32
+    l.aid_last_error.restype = c_char_p
+    l.aid_device_count.restype = c_int32
+    l.aid_launch_count.restype = c_int64
+    l.aid_reset_launch_count.restype = None
+    l.aid_score_packed_bytes.restype = c_size_t
+    l.aid_score_packed_bytes.argtypes = [P(AidScoreDims)]
+    l.aid_score_num_params.restype = c_int32
+    l.aid_score_num_params.argtypes = [P(AidScoreDims)]
+    l.aid_score_pack.restype = c_int32
+    l.aid_score_pack.argtypes = [P(AidScoreDims), P(c_void_p), c_int32, c_void_p, c_size_t, c_void_p]
+    l.aid_score_workspace_bytes.restype = c_size_t
+    l.aid_score_workspace_bytes.argtypes = [P(AidScoreDims), c_int32, c_int32]
+    l.aid_score_forward.restype = c_int32
+    l.aid_score_forward.argtypes = [P(AidScoreDims), c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+                                    c_void_p, c_int32, c_int32, c_void_p, c_void_p]
+    l.aid_sample.restype = c_int32
+    l.aid_sample.argtypes = [P(AidScoreDims), c_void_p, c_void_p, c_size_t, c_int32, c_int32,
+                             P(c_float), P(c_int32), P(c_float), c_int32, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_void_p]
+    l.aid_linear_workspace_bytes.restype = c_size_t
+    l.aid_linear_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
+    l.aid_linear.restype = c_int32
+    l.aid_linear.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                             c_int32, c_int32, c_void_p, c_size_t, c_void_p]
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA extension; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        _declare(l)
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().aid_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed: {msg}")
+
+
+def require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("active_inference_diffusion_b200 runs on CUDA (sm_100a) only: got a "
+                               f"{t.device} tensor; there is no CPU fallback")
+        dev = t.device if dev is None else dev
+    if dev is None:
+        raise RuntimeError("no tensor given")
+    return dev
+
+
+def f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().aid_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().aid_reset_launch_count()
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None, act: int = 0,
+           via_packed: bool = False) -> torch.Tensor:
+    """y = act(x W^T + b) through the tcgen05 GEMM (test primitive)."""
+    dev = require_cuda(x, w, b)
+    x, w, b = f32c(x), f32c(w), f32c(b)
+    M, K = x.shape
+    N = w.shape[0]
+    l = lib()
+    ws_bytes = l.aid_linear_workspace_bytes(M, N, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    y = torch.empty(M, N, dtype=torch.float32, device=dev)
+    check(l.aid_linear(ptr(x), ptr(w), ptr(b), ptr(y), M, N, K, act, int(via_packed), ptr(ws), ws_bytes,
+                       stream_ptr(dev)), "aid_linear")
+    return y

@@ -1,0 +1,687 @@
+// libaid_sm100.so — host orchestration and C ABI (see include/aid_b200.h).
+// Everything numeric runs in the kernels of gemm.cuh / elementwise.cuh; this file only lays
+// out buffers and enqueues launches on the caller's stream.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/aid_b200.h"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+using namespace aid;
+
+// ------------------------------------------------------------------------------------------
+// errors / bookkeeping
+static thread_local std::string g_err;
+static thread_local long long g_launches = 0;
+
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return -1;
+}
+#define AID_CHECK(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return fail(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+  } while (0)
+#define AID_LAUNCH_CHECK(name)                                                            \
+  do {                                                                                    \
+    ++g_launches;                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) return fail(std::string(name) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+#define AID_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != 0) return _r;      \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+static int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  return sms;
+}
+
+static int ew_grid(size_t work_items, int block = 256) {
+  size_t g = (work_items + block - 1) / block;
+  size_t cap = (size_t)num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// ------------------------------------------------------------------------------------------
+// bump allocator over a caller-owned buffer (also used in "measure" mode with base == null)
+struct Arena {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Arena(void* b) : base(static_cast<uint8_t*>(b)) {}
+  template <class T>
+  T* take(size_t bytes) {
+    off = align_up(off, 1024);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+static size_t packed_tiles_bytes(int rows, int cols) {
+  return (size_t)ceil_div(rows, TILE_M) * ceil_div(cols, TILE_K) * TILE_BYTES;
+}
+static size_t tiled_bytes(int rows, int cols) {
+  return (size_t)ceil_div(rows, TILE_M) * (ceil_div(cols, TILE_N) * TILE_N) * TILE_M * 4;
+}
+static size_t stats_bytes(int rows, int cols) {
+  return (size_t)ceil_div(rows, TILE_M) * ceil_div(cols, TILE_N) * TILE_M * sizeof(float2);
+}
+
+// ------------------------------------------------------------------------------------------
+// packed Linear: weight tiles + padded fp32 bias
+struct PLin {
+  const uint8_t* w = nullptr;
+  const float* b = nullptr;
+  int n = 0, k = 0;        // logical [n, k]
+  int n_tiles = 0, kb = 0; // padded tile counts
+};
+
+static void plin_shape(PLin& p, int n, int k, bool modln = false) {
+  p.n = n;
+  p.k = k;
+  p.kb = ceil_div(k, TILE_K);
+  p.n_tiles = modln ? ceil_div(n / 2, 64) : ceil_div(n, TILE_N);
+}
+static size_t plin_w_bytes(const PLin& p) { return (size_t)p.n_tiles * p.kb * TILE_BYTES; }
+static size_t plin_b_bytes(const PLin& p) { return (size_t)p.n_tiles * TILE_N * sizeof(float); }
+
+static int pack_linear(const PLin& p, const float* w, const float* b, int mode, int H, cudaStream_t st) {
+  size_t chunks = (size_t)p.n_tiles * p.kb * 1024;
+  k_pack_rows<<<ew_grid(chunks), 256, 0, st>>>(
+      w, p.n, p.k, p.k, reinterpret_cast<__nv_bfloat16*>(const_cast<uint8_t*>(p.w)), p.n_tiles, p.kb,
+      mode, H);
+  AID_LAUNCH_CHECK("k_pack_rows(weight)");
+  int n_pad = p.n_tiles * TILE_N;
+  k_pack_bias<<<ceil_div(n_pad, 256), 256, 0, st>>>(b, p.n, const_cast<float*>(p.b), n_pad, mode, H);
+  AID_LAUNCH_CHECK("k_pack_bias");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM launch
+template <int EPI, int G, bool RES>
+static int launch_gemm_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = gemm_kernel<EPI, G, RES>;
+  if (!configured) {
+    AID_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    configured = true;
+  }
+  const int a_bytes = RES ? ga.kb * TILE_BYTES : 0;
+  int ring = (SMEM_LIMIT - 1024 - SMEM_CTRL - a_bytes) / TILE_BYTES;
+  if (ring > MAX_RING) ring = MAX_RING;
+  if (ring < G + 2) return fail("gemm: not enough shared memory for the ring");
+  const size_t smem = 1024 + SMEM_CTRL + a_bytes + (size_t)ring * TILE_BYTES;
+  const int units = ga.row_tiles * (ga.n_tiles / G);
+  int grid = units < num_sms() ? units : num_sms();
+  if (grid < 1) return 0;
+  kern<<<grid, GEMM_THREADS, smem, st>>>(ga, ea, ring);
+  AID_LAUNCH_CHECK("gemm_kernel");
+  return 0;
+}
+
+template <int EPI>
+static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs ea, cudaStream_t st,
+                       int* err_flag) {
+  GemmArgs ga;
+  ga.A = A;
+  ga.B = w.w;
+  ga.row_tiles = row_tiles;
+  ga.kb = w.kb;
+  ga.n_tiles = w.n_tiles;
+  ga.err = err_flag;
+  if (!ea.bias) ea.bias = w.b;
+  const bool res = w.kb <= MAX_RES_KB;
+  if (res) return launch_gemm_inst<EPI, 1, true>(ga, ea, st);
+  // streamed A: accumulate as many n-tiles concurrently as TMEM allows so A is read once
+  if (w.n_tiles % 4 == 0) return launch_gemm_inst<EPI, 4, false>(ga, ea, st);
+  if (w.n_tiles % 2 == 0) return launch_gemm_inst<EPI, 2, false>(ga, ea, st);
+  return launch_gemm_inst<EPI, 1, false>(ga, ea, st);
+}
+
+static EpiArgs epi_zero() {
+  EpiArgs e;
+  memset(&e, 0, sizeof(e));
+  e.tw_scalar = 1.0f;
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------
+// Score network: packed layout
+struct ScoreBlockW {
+  PLin mod1, attn, mod2, fc1, fc2;
+};
+struct ScoreW {
+  int L, O, H, E, NB;
+  PLin te1, te3, oe0, oe4, oe7, ce2, ce4, lp, nf, out0, out2;
+  std::vector<ScoreBlockW> blk;
+  // fp32 vectors / scalars copied verbatim
+  const float *oe1_g, *oe1_b, *oe5_g, *oe5_b, *oe8_g, *oe8_b, *ce0_w, *ce0_b;
+  const float *time_scale, *out_mult, *freq_scale;
+  size_t total = 0;
+};
+
+static int score_dims_ok(const AidScoreDims* d) {
+  if (!d) return fail("dims is null");
+  if (d->hidden_dim <= 0 || d->hidden_dim % 64) return fail("hidden_dim must be a positive multiple of 64");
+  if (d->time_embed_dim <= 0 || d->time_embed_dim % 64) return fail("time_embed_dim must be a multiple of 64");
+  if (d->latent_dim <= 0 || d->latent_dim % 4) return fail("latent_dim must be a positive multiple of 4");
+  if (d->obs_dim <= 0) return fail("obs_dim must be positive");
+  if (d->num_blocks < 0 || d->num_blocks > 64) return fail("num_blocks out of range");
+  return 0;
+}
+
+static void score_layout(const AidScoreDims* d, void* packed, ScoreW& s) {
+  s.L = d->latent_dim; s.O = d->obs_dim; s.H = d->hidden_dim; s.E = d->time_embed_dim; s.NB = d->num_blocks;
+  const int H = s.H;
+  Arena a(packed);
+  auto place = [&](PLin& p, int n, int k, bool modln = false) {
+    plin_shape(p, n, k, modln);
+    p.w = a.take<uint8_t>(plin_w_bytes(p));
+    p.b = a.take<float>(plin_b_bytes(p));
+  };
+  place(s.te1, 2 * H, s.E);
+  place(s.te3, H, 2 * H);
+  place(s.oe0, H, s.O);
+  place(s.oe4, H, H);
+  place(s.oe7, H, H);
+  place(s.ce2, s.E, s.E);
+  place(s.ce4, H, s.E);
+  place(s.lp, H, s.L);
+  place(s.nf, 2 * H, H, true);
+  place(s.out0, H / 2, H);
+  place(s.out2, s.L, H / 2);
+  s.blk.resize(s.NB);
+  for (auto& b : s.blk) {
+    place(b.mod1, 2 * H, H, true);
+    place(b.attn, H, H);
+    place(b.mod2, 2 * H, H, true);
+    place(b.fc1, 4 * H, H);
+    place(b.fc2, H, 4 * H);
+  }
+  auto vec = [&](int n) { return a.take<float>((size_t)n * sizeof(float)); };
+  s.oe1_g = vec(H); s.oe1_b = vec(H); s.oe5_g = vec(H); s.oe5_b = vec(H); s.oe8_g = vec(H); s.oe8_b = vec(H);
+  s.ce0_w = vec(s.E); s.ce0_b = vec(s.E);
+  s.time_scale = vec(1); s.out_mult = vec(1); s.freq_scale = vec(1);
+  s.total = align_up(a.off, 1024);
+}
+
+extern "C" size_t aid_score_packed_bytes(const AidScoreDims* dims) {
+  if (score_dims_ok(dims)) return 0;
+  ScoreW s;
+  score_layout(dims, nullptr, s);
+  return s.total;
+}
+
+extern "C" int32_t aid_score_num_params(const AidScoreDims* dims) {
+  if (score_dims_ok(dims)) return -1;
+  return AID_SP_BLOCK0 + dims->num_blocks * AID_SP_BLOCK_STRIDE;
+}
+
+extern "C" int32_t aid_score_pack(const AidScoreDims* dims, const float* const* P, int32_t num_params,
+                                  void* packed, size_t packed_bytes, void* stream) {
+  AID_TRY(score_dims_ok(dims));
+  if (!P || !packed) return fail("aid_score_pack: null pointer");
+  if (num_params != aid_score_num_params(dims)) return fail("aid_score_pack: wrong parameter count");
+  ScoreW s;
+  score_layout(dims, packed, s);
+  if (packed_bytes < s.total) return fail("aid_score_pack: packed buffer too small");
+  for (int i = 0; i < num_params; ++i)
+    if (!P[i]) return fail("aid_score_pack: null parameter pointer at index " + std::to_string(i));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int H = s.H;
+  AID_TRY(pack_linear(s.te1, P[AID_SP_TE1_W], P[AID_SP_TE1_B], MAP_PLAIN, H, st));
+  AID_TRY(pack_linear(s.te3, P[AID_SP_TE3_W], P[AID_SP_TE3_B], MAP_PLAIN, H, st));
+  AID_TRY(pack_linear(s.oe0, P[AID_SP_OE0_W], P[AID_SP_OE0_B], MAP_PLAIN, H, st));
+  AID_TRY(pack_linear(s.oe4, P[AID_SP_OE4_W], P[AID_SP_OE4_B], MAP_PLAIN, H, st));
+  AID_TRY(pack_linear(s.oe7, P[AID_SP_OE7_W], P[AID_SP_OE7_B], MAP_PLAIN, H, st));
+  AID_TRY(pack_linear(s.ce2, P[AID_SP_CE2_W], P[AID_SP_CE2_B], MAP_PLAIN, H, st));
+  AID_TRY(pack_linear(s.ce4, P[AID_SP_CE4_W], P[AID_SP_CE4_B], MAP_PLAIN, H, st));
+  AID_TRY(pack_linear(s.lp, P[AID_SP_LP_W], P[AID_SP_LP_B], MAP_PLAIN, H, st));
+  AID_TRY(pack_linear(s.nf, P[AID_SP_NF_W], P[AID_SP_NF_B], MAP_MODLN, H, st));
+  AID_TRY(pack_linear(s.out0, P[AID_SP_OUT0_W], P[AID_SP_OUT0_B], MAP_PLAIN, H, st));
+  AID_TRY(pack_linear(s.out2, P[AID_SP_OUT2_W], nullptr, MAP_PLAIN, H, st));
+  for (int i = 0; i < s.NB; ++i) {
+    const float* const* B = P + AID_SP_BLOCK0 + i * AID_SP_BLOCK_STRIDE;
+    ScoreBlockW& b = s.blk[i];
+    AID_TRY(pack_linear(b.mod1, B[AID_SPB_N1_W], B[AID_SPB_N1_B], MAP_MODLN, H, st));
+    AID_TRY(pack_linear(b.mod2, B[AID_SPB_N2_W], B[AID_SPB_N2_B], MAP_MODLN, H, st));
+    size_t chunks = (size_t)b.attn.n_tiles * b.attn.kb * 1024;
+    k_pack_folded_attn<<<ew_grid(chunks, 128), 128, 0, st>>>(
+        B[AID_SPB_INPROJ_W], B[AID_SPB_OUTPROJ_W], H,
+        reinterpret_cast<__nv_bfloat16*>(const_cast<uint8_t*>(b.attn.w)), b.attn.n_tiles, b.attn.kb);
+    AID_LAUNCH_CHECK("k_pack_folded_attn");
+    int n_pad = b.attn.n_tiles * TILE_N;
+    k_folded_attn_bias<<<ceil_div(n_pad, 128), 128, 0, st>>>(
+        B[AID_SPB_INPROJ_B], B[AID_SPB_OUTPROJ_W], B[AID_SPB_OUTPROJ_B], H, const_cast<float*>(b.attn.b), n_pad);
+    AID_LAUNCH_CHECK("k_folded_attn_bias");
+    AID_TRY(pack_linear(b.fc1, B[AID_SPB_FC1_W], B[AID_SPB_FC1_B], MAP_PLAIN, H, st));
+    AID_TRY(pack_linear(b.fc2, B[AID_SPB_FC2_W], B[AID_SPB_FC2_B], MAP_PLAIN, H, st));
+  }
+  auto copyv = [&](const float* dst, const float* src, int n) {
+    return cudaMemcpyAsync(const_cast<float*>(dst), src, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  };
+  AID_CHECK(copyv(s.oe1_g, P[AID_SP_OE1_G], H)); AID_CHECK(copyv(s.oe1_b, P[AID_SP_OE1_B], H));
+  AID_CHECK(copyv(s.oe5_g, P[AID_SP_OE5_G], H)); AID_CHECK(copyv(s.oe5_b, P[AID_SP_OE5_B], H));
+  AID_CHECK(copyv(s.oe8_g, P[AID_SP_OE8_G], H)); AID_CHECK(copyv(s.oe8_b, P[AID_SP_OE8_B], H));
+  AID_CHECK(copyv(s.ce0_w, P[AID_SP_CE0_W], s.E)); AID_CHECK(copyv(s.ce0_b, P[AID_SP_CE0_B], s.E));
+  AID_CHECK(copyv(s.time_scale, P[AID_SP_TIME_SCALE], 1));
+  AID_CHECK(copyv(s.out_mult, P[AID_SP_OUTPUT_MULTIPLIER], 1));
+  AID_CHECK(copyv(s.freq_scale, P[AID_SP_FREQ_SCALE], 1));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Score network: workspace + forward pieces
+struct ScoreWS {
+  int B, RT;          // batch rows / row tiles
+  int TR, TRT;        // time-table rows / row tiles (per-row times: TR == B)
+  __nv_bfloat16 *zp, *obsp, *xn, *act, *o1, *csilu, *obs_h;   // batch-sized packed operands
+  float4 *h, *obs_emb, *obs_y;                                 // batch-sized tiled fp32
+  float2 *h_stats, *obs_stats;
+  __nv_bfloat16 *te_e, *te_h, *ce_a, *ce_b;                    // time-table packed operands
+  float4 *tsin, *tcont;                                        // time-table tiled fp32
+  float *t_sin_arg, *t_norm, *t_flag, *t_w;                    // time-table per-row scalars
+  int* err;
+  size_t total;
+};
+
+static void score_ws_layout(const ScoreW& s, int batch, int table_rows, void* ws, ScoreWS& w) {
+  const int H = s.H;
+  w.B = batch; w.RT = ceil_div(batch, TILE_M);
+  w.TR = table_rows; w.TRT = ceil_div(table_rows, TILE_M);
+  Arena a(ws);
+  w.err = a.take<int>(1024);
+  w.zp = a.take<__nv_bfloat16>(packed_tiles_bytes(batch, s.L));
+  w.obsp = a.take<__nv_bfloat16>(packed_tiles_bytes(batch, s.O));
+  w.xn = a.take<__nv_bfloat16>(packed_tiles_bytes(batch, H));
+  w.act = a.take<__nv_bfloat16>(packed_tiles_bytes(batch, 4 * H));
+  w.o1 = a.take<__nv_bfloat16>(packed_tiles_bytes(batch, H / 2));
+  w.csilu = a.take<__nv_bfloat16>(packed_tiles_bytes(batch, H));
+  w.obs_h = a.take<__nv_bfloat16>(packed_tiles_bytes(batch, H));
+  w.h = a.take<float4>(tiled_bytes(batch, H));
+  w.obs_emb = a.take<float4>(tiled_bytes(batch, H));
+  w.obs_y = a.take<float4>(tiled_bytes(batch, H));
+  w.h_stats = a.take<float2>(stats_bytes(batch, H));
+  w.obs_stats = a.take<float2>(stats_bytes(batch, H));
+  w.te_e = a.take<__nv_bfloat16>(packed_tiles_bytes(table_rows, s.E));
+  w.te_h = a.take<__nv_bfloat16>(packed_tiles_bytes(table_rows, 2 * H));
+  w.ce_a = a.take<__nv_bfloat16>(packed_tiles_bytes(table_rows, s.E));
+  w.ce_b = a.take<__nv_bfloat16>(packed_tiles_bytes(table_rows, s.E));
+  w.tsin = a.take<float4>(tiled_bytes(table_rows, H));
+  w.tcont = a.take<float4>(tiled_bytes(table_rows, H));
+  w.t_sin_arg = a.take<float>((size_t)table_rows * 4);
+  w.t_norm = a.take<float>((size_t)table_rows * 4);
+  w.t_flag = a.take<float>((size_t)table_rows * 4);
+  w.t_w = a.take<float>((size_t)table_rows * 4);
+  w.total = align_up(a.off, 1024);
+}
+
+extern "C" size_t aid_score_workspace_bytes(const AidScoreDims* dims, int32_t batch, int32_t table_rows) {
+  if (score_dims_ok(dims) || batch <= 0) return 0;
+  if (table_rows <= 0) table_rows = batch;
+  ScoreW s;
+  score_layout(dims, nullptr, s);
+  ScoreWS w;
+  score_ws_layout(s, batch, table_rows, nullptr, w);
+  return w.total;
+}
+
+// per-row time arguments for the score net's two branches (models/score_networks.py:121-141)
+__global__ void k_time_args(const float* __restrict__ t, int rows, int continuous,
+                            float* __restrict__ sin_arg, float* __restrict__ t_norm,
+                            float* __restrict__ flag, float* __restrict__ tw) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  float ti = t[i];
+  if (continuous) {
+    sin_arg[i] = __fmul_rn(ti, 999.0f);
+    t_norm[i] = __fsub_rn(__fmul_rn(2.0f, ti), 1.0f);
+    flag[i] = 1.f;
+    tw[i] = __fsqrt_rn(__fdiv_rn(1.0f, __fadd_rn(1e-5f, ti)));
+  } else {
+    sin_arg[i] = ti;
+    t_norm[i] = 0.f;
+    flag[i] = 0.f;
+    tw[i] = 1.f;
+  }
+}
+
+// time_embed (+ continuous_time_embed) over `w.TR` rows whose args are already in w.t_*.
+static int run_time_table(const ScoreW& s, ScoreWS& w, bool any_continuous, cudaStream_t st) {
+  const int H = s.H;
+  k_sincos_pack<<<ew_grid((size_t)w.TRT * (s.E / 64) * 1024), 256, 0, st>>>(
+      w.t_sin_arg, w.TR, s.freq_scale, s.E, w.te_e, w.TRT);
+  AID_LAUNCH_CHECK("k_sincos_pack");
+  EpiArgs e = epi_zero();
+  e.act = ACT_SILU; e.n_valid = 2 * H; e.rows_valid = w.TR; e.out_packed = w.te_h; e.out_kb = 2 * H / 64;
+  AID_TRY(launch_gemm<EPI_PACK>(reinterpret_cast<uint8_t*>(w.te_e), w.TRT, s.te1, e, st, w.err));
+  e = epi_zero();
+  e.n_valid = H; e.rows_valid = w.TR; e.out_tiled = w.tsin; e.ld4 = s.te3.n_tiles * TILE_N / 4;
+  AID_TRY(launch_gemm<EPI_F32>(reinterpret_cast<uint8_t*>(w.te_h), w.TRT, s.te3, e, st, w.err));
+  if (any_continuous) {
+    k_cont0_pack<<<ew_grid((size_t)w.TRT * (s.E / 64) * 1024), 256, 0, st>>>(
+        w.t_norm, w.TR, s.ce0_w, s.ce0_b, s.E, w.ce_a, w.TRT);
+    AID_LAUNCH_CHECK("k_cont0_pack");
+    e = epi_zero();
+    e.act = ACT_SILU; e.n_valid = s.E; e.rows_valid = w.TR; e.out_packed = w.ce_b; e.out_kb = s.E / 64;
+    AID_TRY(launch_gemm<EPI_PACK>(reinterpret_cast<uint8_t*>(w.ce_a), w.TRT, s.ce2, e, st, w.err));
+    e = epi_zero();
+    e.n_valid = H; e.rows_valid = w.TR; e.out_tiled = w.tcont; e.ld4 = s.ce4.n_tiles * TILE_N / 4;
+    AID_TRY(launch_gemm<EPI_F32>(reinterpret_cast<uint8_t*>(w.ce_b), w.TRT, s.ce4, e, st, w.err));
+  }
+  return 0;
+}
+
+// obs_encoder (models/score_networks.py:49-59, eval mode) -> w.obs_emb (tiled fp32)
+static int run_obs_encoder(const ScoreW& s, ScoreWS& w, const float* obs, cudaStream_t st) {
+  const int H = s.H;
+  const int ld4 = ceil_div(H, TILE_N) * TILE_N / 4;
+  const int nt = ceil_div(H, TILE_N);
+  if (!obs) {
+    AID_CHECK(cudaMemsetAsync(w.obs_emb, 0, tiled_bytes(w.B, H), st));
+    return 0;
+  }
+  const int kbo = ceil_div(s.O, TILE_K);
+  k_pack_rows<<<ew_grid((size_t)w.RT * kbo * 1024), 256, 0, st>>>(obs, w.B, s.O, s.O, w.obsp, w.RT, kbo,
+                                                                   MAP_PLAIN, 0);
+  AID_LAUNCH_CHECK("k_pack_rows(obs)");
+  const PLin* lin[3] = {&s.oe0, &s.oe4, &s.oe7};
+  const float* g[3] = {s.oe1_g, s.oe5_g, s.oe8_g};
+  const float* b[3] = {s.oe1_b, s.oe5_b, s.oe8_b};
+  const uint8_t* a_in = reinterpret_cast<uint8_t*>(w.obsp);
+  for (int i = 0; i < 3; ++i) {
+    EpiArgs e = epi_zero();
+    e.n_valid = H; e.rows_valid = w.B; e.out_tiled = w.obs_y; e.ld4 = ld4; e.stats_out = w.obs_stats;
+    AID_TRY(launch_gemm<EPI_F32>(a_in, w.RT, *lin[i], e, st, w.err));
+    LnArgs l;
+    l.x = w.obs_y; l.stats = w.obs_stats; l.stats_nt = nt; l.ld4 = ld4; l.n = H;
+    l.gamma = g[i]; l.beta = b[i];
+    l.act = (i < 2) ? ACT_SILU : ACT_NONE;
+    l.out_packed = (i < 2) ? w.obs_h : nullptr;
+    l.out_tiled = (i < 2) ? nullptr : w.obs_emb;
+    k_ln_act<<<dim3(w.RT, ceil_div(H, 64)), 128, 0, st>>>(l);
+    AID_LAUNCH_CHECK("k_ln_act");
+    a_in = reinterpret_cast<uint8_t*>(w.obs_h);
+  }
+  return 0;
+}
+
+struct StepOut {
+  // EPI_SCORE configuration for the last GEMM
+  int do_step = 0;
+  const float* tw_rows = nullptr;
+  float tw_scalar = 1.0f;
+  const float* z_in = nullptr;
+  const float* eps = nullptr;
+  float c_s1 = 0, c_ra = 0, c_c1 = 0, c_c2 = 0, c_sigma = 0;
+  float* z_out = nullptr;
+  __nv_bfloat16* z_packed_out = nullptr;
+};
+
+// Trunk of the score net: w.zp (packed z) and w.csilu (packed SiLU(conditioning)) are ready.
+// models/score_networks.py:156-170 with the attention folded (see k_pack_folded_attn).
+static int run_score_trunk(const ScoreW& s, ScoreWS& w, const StepOut& o, cudaStream_t st) {
+  const int H = s.H;
+  const int ld4 = ceil_div(H, TILE_N) * TILE_N / 4;
+  const int nt_h = ceil_div(H, TILE_N);
+  const uint8_t* zp = reinterpret_cast<uint8_t*>(w.zp);
+  const uint8_t* cs = reinterpret_cast<uint8_t*>(w.csilu);
+  const uint8_t* xn = reinterpret_cast<uint8_t*>(w.xn);
+
+  auto f32_out = [&](const PLin& lin, const uint8_t* a, bool resid) {
+    EpiArgs e = epi_zero();
+    e.n_valid = H; e.rows_valid = w.B; e.out_tiled = w.h; e.ld4 = ld4; e.stats_out = w.h_stats;
+    e.resid_tiled = resid ? w.h : nullptr;
+    return launch_gemm<EPI_F32>(a, w.RT, lin, e, st, w.err);
+  };
+  auto modln = [&](const PLin& lin) {
+    EpiArgs e = epi_zero();
+    e.rows_valid = w.B; e.n_valid = 2 * H; e.out_packed = w.xn; e.out_kb = H / 64;
+    e.h_tiled = w.h; e.h_ld4 = ld4; e.stats_in = w.h_stats; e.stats_nt = nt_h; e.h_dim = H;
+    return launch_gemm<EPI_MODLN>(cs, w.RT, lin, e, st, w.err);
+  };
+
+  AID_TRY(f32_out(s.lp, zp, false));
+  for (int i = 0; i < s.NB; ++i) {
+    const ScoreBlockW& b = s.blk[i];
+    AID_TRY(modln(b.mod1));
+    AID_TRY(f32_out(b.attn, xn, true));
+    AID_TRY(modln(b.mod2));
+    EpiArgs e = epi_zero();
+    e.act = ACT_GELU; e.n_valid = 4 * H; e.rows_valid = w.B; e.out_packed = w.act; e.out_kb = 4 * H / 64;
+    AID_TRY(launch_gemm<EPI_PACK>(xn, w.RT, b.fc1, e, st, w.err));
+    AID_TRY(f32_out(b.fc2, reinterpret_cast<uint8_t*>(w.act), true));
+  }
+  AID_TRY(modln(s.nf));
+  EpiArgs e = epi_zero();
+  e.act = ACT_SILU; e.n_valid = H / 2; e.rows_valid = w.B; e.out_packed = w.o1; e.out_kb = ceil_div(H / 2, 64);
+  AID_TRY(launch_gemm<EPI_PACK>(xn, w.RT, s.out0, e, st, w.err));
+  e = epi_zero();
+  e.bias = nullptr;  // output_proj.2 has no bias; launch_gemm substitutes the zero-padded vector
+  e.n_valid = s.L; e.rows_valid = w.B;
+  e.out_mult = s.out_mult; e.tw_rows = o.tw_rows; e.tw_scalar = o.tw_scalar;
+  e.do_step = o.do_step; e.z_in = o.z_in; e.eps = o.eps;
+  e.c_s1 = o.c_s1; e.c_ra = o.c_ra; e.c_c1 = o.c_c1; e.c_c2 = o.c_c2; e.c_sigma = o.c_sigma;
+  e.z_out = o.z_out; e.out_packed = o.z_packed_out; e.out_kb = ceil_div(s.L, 64);
+  AID_TRY(launch_gemm<EPI_SCORE>(reinterpret_cast<uint8_t*>(w.o1), w.RT, s.out2, e, st, w.err));
+  return 0;
+}
+
+static int run_cond(const ScoreW& s, ScoreWS& w, bool use_cont, int fixed_row, cudaStream_t st) {
+  CondArgs c;
+  c.t_sin = w.tsin;
+  c.t_cont = use_cont ? w.tcont : nullptr;
+  c.cont_flag = use_cont ? w.t_flag : nullptr;
+  c.time_scale = s.time_scale;
+  c.obs_emb = w.obs_emb;
+  c.fixed_row = fixed_row;
+  c.ld4 = ceil_div(s.H, TILE_N) * TILE_N / 4;
+  c.H = s.H;
+  c.rows = w.B;
+  c.row_tiles = w.RT;
+  c.out_packed = w.csilu;
+  c.out_tiled = nullptr;
+  k_cond<<<ew_grid((size_t)w.RT * c.ld4 * TILE_M), 256, 0, st>>>(c);
+  AID_LAUNCH_CHECK("k_cond");
+  return 0;
+}
+
+extern "C" int32_t aid_score_forward(const AidScoreDims* dims, const void* packed, void* workspace,
+                                     size_t workspace_bytes, const float* z_t, const float* time,
+                                     const float* observation, int32_t batch, int32_t continuous,
+                                     float* score_out, void* stream) {
+  AID_TRY(score_dims_ok(dims));
+  if (!packed || !workspace || !z_t || !time || !score_out) return fail("aid_score_forward: null pointer");
+  if (batch <= 0) return fail("aid_score_forward: batch must be positive");
+  ScoreW s;
+  score_layout(dims, const_cast<void*>(packed), s);
+  ScoreWS w;
+  score_ws_layout(s, batch, batch, workspace, w);
+  if (workspace_bytes < w.total) return fail("aid_score_forward: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AID_CHECK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
+  k_time_args<<<ceil_div(batch, 256), 256, 0, st>>>(time, batch, continuous, w.t_sin_arg, w.t_norm, w.t_flag, w.t_w);
+  AID_LAUNCH_CHECK("k_time_args");
+  AID_TRY(run_time_table(s, w, continuous != 0, st));
+  AID_TRY(run_obs_encoder(s, w, observation, st));
+  AID_TRY(run_cond(s, w, continuous != 0, -1, st));
+  const int kbl = ceil_div(s.L, TILE_K);
+  k_pack_rows<<<ew_grid((size_t)w.RT * kbl * 1024), 256, 0, st>>>(z_t, batch, s.L, s.L, w.zp, w.RT, kbl, MAP_PLAIN, 0);
+  AID_LAUNCH_CHECK("k_pack_rows(z)");
+  StepOut o;
+  o.do_step = 0;
+  o.tw_rows = continuous ? w.t_w : nullptr;
+  o.tw_scalar = 1.0f;
+  o.z_out = score_out;
+  return run_score_trunk(s, w, o, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Reverse diffusion
+extern "C" int32_t aid_sample(const AidScoreDims* dims, const void* packed, void* workspace,
+                              size_t workspace_bytes, int32_t batch, int32_t n_steps,
+                              const float* step_time_host, const int32_t* step_index_host,
+                              const float* coef_host, int32_t T, const float* observation,
+                              const float* z_init, const float* noise, float* z_out, float* traj_out,
+                              void* stream) {
+  AID_TRY(score_dims_ok(dims));
+  if (!packed || !workspace || !z_init || !z_out || !step_time_host || !step_index_host || !coef_host)
+    return fail("aid_sample: null pointer");
+  if (batch <= 0 || n_steps <= 0 || T <= 0) return fail("aid_sample: batch, n_steps and T must be positive");
+  ScoreW s;
+  score_layout(dims, const_cast<void*>(packed), s);
+  ScoreWS w;
+  score_ws_layout(s, batch, n_steps, workspace, w);
+  if (workspace_bytes < w.total) return fail("aid_sample: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AID_CHECK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
+
+  // Per-step time arguments, evaluated on the host in fp32 exactly as the reference's tensor ops
+  // would (models/score_networks.py:121-137).  The branch is batch-global and the batch is
+  // time-constant, so it is resolved per step here without a device sync.
+  std::vector<float> sin_arg(n_steps), tn(n_steps), flag(n_steps), tw(n_steps);
+  bool any_cont = false;
+  for (int i = 0; i < n_steps; ++i) {
+    const float t = step_time_host[i];
+    const bool cont = (t <= 1.0f) && (t >= 0.0f);
+    if (step_index_host[i] < 0 || step_index_host[i] >= T) return fail("aid_sample: step index out of range");
+    if (cont) {
+      volatile float a = t * 999.0f;
+      volatile float b = 2.0f * t;
+      volatile float c = b - 1.0f;
+      volatile float d = 1e-5f + t;
+      volatile float e = 1.0f / d;
+      sin_arg[i] = a; tn[i] = c; flag[i] = 1.f; tw[i] = sqrtf(e);
+      any_cont = true;
+    } else {
+      sin_arg[i] = t; tn[i] = 0.f; flag[i] = 0.f; tw[i] = 1.f;
+    }
+  }
+  AID_CHECK(cudaMemcpyAsync(w.t_sin_arg, sin_arg.data(), n_steps * 4, cudaMemcpyHostToDevice, st));
+  AID_CHECK(cudaMemcpyAsync(w.t_norm, tn.data(), n_steps * 4, cudaMemcpyHostToDevice, st));
+  AID_CHECK(cudaMemcpyAsync(w.t_flag, flag.data(), n_steps * 4, cudaMemcpyHostToDevice, st));
+  AID_TRY(run_time_table(s, w, any_cont, st));
+  AID_TRY(run_obs_encoder(s, w, observation, st));
+
+  const int kbl = ceil_div(s.L, TILE_K);
+  k_pack_rows<<<ew_grid((size_t)w.RT * kbl * 1024), 256, 0, st>>>(z_init, batch, s.L, s.L, w.zp, w.RT, kbl, MAP_PLAIN, 0);
+  AID_LAUNCH_CHECK("k_pack_rows(z)");
+  const size_t zl = (size_t)batch * s.L;
+  if (traj_out) AID_CHECK(cudaMemcpyAsync(traj_out, z_init, zl * 4, cudaMemcpyDeviceToDevice, st));
+
+  const float* z_cur = z_init;
+  int draw = 0;
+  for (int i = 0; i < n_steps; ++i) {
+    const int ti = step_index_host[i];
+    AID_TRY(run_cond(s, w, flag[i] != 0.f, i, st));
+    StepOut o;
+    o.do_step = 1;
+    o.tw_rows = nullptr;
+    o.tw_scalar = tw[i];
+    o.z_in = z_cur;
+    o.eps = (noise && ti != 0) ? noise + (size_t)(draw++) * zl : nullptr;
+    o.c_s1 = coef_host[0 * T + ti];
+    o.c_ra = coef_host[1 * T + ti];
+    o.c_c1 = coef_host[2 * T + ti];
+    o.c_c2 = coef_host[3 * T + ti];
+    o.c_sigma = coef_host[4 * T + ti];
+    o.z_out = traj_out ? traj_out + (size_t)(i + 1) * zl : z_out;
+    o.z_packed_out = w.zp;
+    AID_TRY(run_score_trunk(s, w, o, st));
+    z_cur = o.z_out;
+  }
+  if (traj_out) AID_CHECK(cudaMemcpyAsync(z_out, z_cur, zl * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Primitive for tests
+__global__ void k_unpack_rows(const __nv_bfloat16* __restrict__ src, int rows, int cols, int kb_total,
+                              float* __restrict__ out, int ld) {
+  size_t total = (size_t)rows * cols;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    int row = (int)(idx / cols), c = (int)(idx % cols);
+    int rt = row >> 7, r = row & 127, kb = c >> 6, cc = c & 63;
+    const __nv_bfloat16* tile = src + ((size_t)rt * kb_total + kb) * TILE_ELEMS;
+    out[(size_t)row * ld + c] = __bfloat162float(tile[packed_off(r, cc)]);
+  }
+}
+
+extern "C" size_t aid_linear_workspace_bytes(int32_t M, int32_t N, int32_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  Arena a(nullptr);
+  PLin p;
+  plin_shape(p, N, K);
+  a.take<int>(1024);
+  a.take<uint8_t>(packed_tiles_bytes(M, K));
+  a.take<uint8_t>(plin_w_bytes(p));
+  a.take<uint8_t>(plin_b_bytes(p));
+  a.take<uint8_t>(packed_tiles_bytes(M, p.n_tiles * TILE_N));
+  return align_up(a.off, 1024);
+}
+
+extern "C" int32_t aid_linear(const float* x, const float* wt, const float* bias, float* y, int32_t M,
+                              int32_t N, int32_t K, int32_t act, int32_t via_packed, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  if (!x || !wt || !y || !workspace) return fail("aid_linear: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0) return fail("aid_linear: bad shape");
+  if (workspace_bytes < aid_linear_workspace_bytes(M, N, K)) return fail("aid_linear: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena a(workspace);
+  PLin p;
+  plin_shape(p, N, K);
+  int* err = a.take<int>(1024);
+  __nv_bfloat16* xp = a.take<__nv_bfloat16>(packed_tiles_bytes(M, K));
+  p.w = a.take<uint8_t>(plin_w_bytes(p));
+  p.b = a.take<float>(plin_b_bytes(p));
+  __nv_bfloat16* yp = a.take<__nv_bfloat16>(packed_tiles_bytes(M, p.n_tiles * TILE_N));
+  AID_CHECK(cudaMemsetAsync(err, 0, sizeof(int), st));
+  const int rt = ceil_div(M, TILE_M);
+  k_pack_rows<<<ew_grid((size_t)rt * p.kb * 1024), 256, 0, st>>>(x, M, K, K, xp, rt, p.kb, MAP_PLAIN, 0);
+  AID_LAUNCH_CHECK("k_pack_rows(x)");
+  AID_TRY(pack_linear(p, wt, bias, MAP_PLAIN, 0, st));
+  EpiArgs e = epi_zero();
+  e.act = act; e.n_valid = N; e.rows_valid = M;
+  if (via_packed) {
+    e.out_packed = yp; e.out_kb = p.n_tiles * 2;
+    AID_TRY(launch_gemm<EPI_PACK>(reinterpret_cast<uint8_t*>(xp), rt, p, e, st, err));
+    k_unpack_rows<<<ew_grid((size_t)M * N), 256, 0, st>>>(yp, M, N, p.n_tiles * 2, y, N);
+    AID_LAUNCH_CHECK("k_unpack_rows");
+  } else {
+    e.out_rm = y; e.ld_rm = N;
+    AID_TRY(launch_gemm<EPI_F32>(reinterpret_cast<uint8_t*>(xp), rt, p, e, st, err));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t aid_abi_version(void) { return AID_ABI_VERSION; }
+extern "C" const char* aid_last_error(void) { return g_err.c_str(); }
+extern "C" int32_t aid_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+extern "C" int64_t aid_launch_count(void) { return g_launches; }
+extern "C" void aid_reset_launch_count(void) { g_launches = 0; }

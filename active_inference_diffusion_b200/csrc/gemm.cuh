@@ -1,0 +1,495 @@
+// Persistent, warp-specialised tcgen05 GEMM with fused epilogues (sm_100a).
+//
+//   D[128 x 128] (TMEM, fp32) = A[128 x K] (bf16, K-major, SW128 tiles) * B[128 x K]^T
+//
+// Data layout in HBM (all produced by this library, never by the caller):
+//   * "packed" bf16 operand  : [row_tile][k_block] tiles of 128 rows x 64 cols, each tile 16 KiB
+//     contiguous and already in the 128-byte-swizzled shared-memory image, so one
+//     cp.async.bulk (TMA engine) moves a tile and the UMMA descriptor reads it directly.
+//   * "tiled" fp32 activation: [row_tile][col/4][128 rows] float4, so that the epilogue's
+//     one-thread-per-row accesses are fully coalesced.
+//   * LayerNorm partials     : [row_tile][n_tile][128 rows] float2 (mean, M2) per 128 columns.
+//
+// Work decomposition: unit = (row_tile, group of G consecutive 128-col n-tiles).  Each CTA
+// (one per SM) takes a contiguous range of units so the A row tile stays resident in shared
+// memory while the weight tiles stream through a ring of 16 KiB stages.
+//
+// Roles (384 threads): warp0 lane0 = bulk-copy producer, warp1 lane0 = MMA issuer,
+// warp2 = TMEM allocator, warps 4..11 = two epilogue groups (tile sequence number parity).
+#pragma once
+#include <cuda_bf16.h>
+#include "ptx.cuh"
+
+namespace aid {
+
+constexpr int TILE_M = 128;
+constexpr int TILE_N = 128;
+constexpr int TILE_K = 64;
+constexpr int TILE_BYTES = TILE_M * TILE_K * 2;  // 16384
+constexpr int TILE_ELEMS = TILE_M * TILE_K;      // 8192
+constexpr int MAX_RES_KB = 8;                    // A resident up to K = 512
+constexpr int MAX_RING = 14;                     // ring stages (16 KiB each)
+constexpr int GEMM_THREADS = 384;
+constexpr int SMEM_LIMIT = 232448;               // 227 KiB opt-in max per CTA
+constexpr int SMEM_CTRL = 1024;                  // barriers + tmem pointer
+
+enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_GELU = 3 };
+
+enum EpiKind : int {
+  EPI_PACK = 0,   // y = act(acc + bias)                -> packed bf16 (next GEMM's A)
+  EPI_F32 = 1,    // y = acc + bias (+ resid)           -> tiled fp32 and/or row-major fp32 (+ LN partials)
+  EPI_MODLN = 2,  // xn = LN(h)*(1+scale)+shift         -> packed bf16   (acc = [scale | shift])
+  EPI_SCORE = 3,  // clamp/scale score, optional reverse-diffusion step -> z (fp32 row-major + packed)
+};
+
+struct GemmArgs {
+  const uint8_t* A;  // packed
+  const uint8_t* B;  // packed
+  int row_tiles;
+  int kb;       // K / 64
+  int n_tiles;  // N_pad / 128
+  int* err;
+};
+
+struct EpiArgs {
+  const float* bias;   // [n_tiles*128] (padded), may be null
+  int act;
+  int n_valid;         // number of real output columns
+  int rows_valid;      // number of real rows (batch)
+  // EPI_PACK / EPI_MODLN / EPI_SCORE(packed z)
+  __nv_bfloat16* out_packed;
+  int out_kb;          // k-blocks per row tile of the packed output
+  // EPI_F32
+  float4* out_tiled;         // may be null
+  const float4* resid_tiled; // may be null
+  int ld4;                   // float4 columns per row of tiled buffers (N_pad/4)
+  float2* stats_out;         // may be null; [rt][n_tiles][128]
+  float* out_rm;             // optional row-major output [rows_valid, ld_rm]
+  int ld_rm;
+  // EPI_MODLN
+  const float4* h_tiled;     // [rt][h_ld4][128]
+  int h_ld4;
+  const float2* stats_in;    // [rt][stats_nt][128]
+  int stats_nt;
+  int h_dim;                 // real hidden width (LayerNorm length)
+  // EPI_SCORE
+  const float* out_mult;     // device scalar (output_multiplier)
+  const float* tw_rows;      // per-row time weight or null
+  float tw_scalar;           // used when tw_rows == null
+  int do_step;               // 0: write score; 1: reverse-diffusion update
+  const float* z_in;         // [rows_valid, n_valid] row-major
+  const float* eps;          // [rows_valid, n_valid] or null (deterministic / t == 0)
+  float c_s1, c_ra, c_c1, c_c2, c_sigma;
+  float* z_out;              // row-major fp32 (score or new z)
+};
+
+__device__ __forceinline__ int packed_off(int r, int c) {  // element offset inside a 128x64 tile
+  return r * TILE_K + ((((c >> 3) ^ (r & 7)) << 3) | (c & 7));
+}
+
+__device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float act_gelu(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+__device__ __forceinline__ float act_apply(float x, int act) {
+  switch (act) {
+    case ACT_SILU: return act_silu(x);
+    case ACT_RELU: return fmaxf(x, 0.0f);
+    case ACT_GELU: return act_gelu(x);
+    default: return x;
+  }
+}
+// `act` is warp-uniform: branch once per 32-column chunk, not once per element.
+__device__ __forceinline__ void act_apply32(float (&y)[32], int act) {
+  if (act == ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = act_silu(y[j]);
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+  } else if (act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = act_gelu(y[j]);
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Write 32 consecutive columns [c0, c0+32) of row r (c0 % 32 == 0) into a packed tile row.
+__device__ __forceinline__ void store_packed32(__nv_bfloat16* tile_base, int r, int c0_in_tile,
+                                               const float (&y)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 v;
+    v.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
+    v.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
+    v.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
+    v.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
+    int chunk = (c0_in_tile >> 3) + q;
+    *reinterpret_cast<uint4*>(tile_base + r * TILE_K + ((chunk ^ (r & 7)) << 3)) = v;
+  }
+}
+
+// Chan/Welford merge of (n_b, mean_b, M2_b) into (n, mean, M2).
+__device__ __forceinline__ void stats_merge(float& n, float& mean, float& m2, float nb, float mb,
+                                            float m2b) {
+  if (nb <= 0.f) return;
+  float nt = n + nb;
+  float d = mb - mean;
+  mean += d * (nb / nt);
+  m2 += m2b + d * d * (n * nb / nt);
+  n = nt;
+}
+
+// ------------------------------------------------------------------------------------------
+// Epilogue for one 128x128 accumulator tile.  `tmem_tile` already carries this warp's lane base.
+// rt/nt: row tile / n-tile indices; r: row inside the tile (== TMEM lane).
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_tile, int rt, int nt,
+                                              int n_tiles, int r) {
+  const int row = rt * TILE_M + r;
+  uint32_t raw[32];
+
+  if constexpr (EPI == EPI_PACK) {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      tmem_ld32(tmem_tile + c * 32, raw);
+      tmem_ld_wait();
+      const int n0 = nt * TILE_N + c * 32;
+      float y[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        y[j] = __uint_as_float(raw[j]) + (e.bias ? __ldg(e.bias + n0 + j) : 0.f);
+      act_apply32(y, e.act);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) y[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
+      const int kb_out = n0 >> 6;
+      if (kb_out < e.out_kb) {
+        __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
+        store_packed32(tile, r, n0 & 63, y);
+      }
+    }
+  } else if constexpr (EPI == EPI_F32) {
+    float sn = 0.f, smean = 0.f, sm2 = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      tmem_ld32(tmem_tile + c * 32, raw);
+      tmem_ld_wait();
+      const int n0 = nt * TILE_N + c * 32;
+      float y[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        y[j] = __uint_as_float(raw[j]) + (e.bias ? __ldg(e.bias + n0 + j) : 0.f);
+      if (e.resid_tiled) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 hv = e.resid_tiled[((size_t)rt * e.ld4 + (n0 >> 2) + q) * TILE_M + r];
+          y[q * 4 + 0] += hv.x; y[q * 4 + 1] += hv.y; y[q * 4 + 2] += hv.z; y[q * 4 + 3] += hv.w;
+        }
+      }
+      act_apply32(y, e.act);
+      if (e.out_tiled) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          e.out_tiled[((size_t)rt * e.ld4 + (n0 >> 2) + q) * TILE_M + r] =
+              make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+      }
+      if (e.out_rm && row < e.rows_valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < e.n_valid) e.out_rm[(size_t)row * e.ld_rm + n0 + j] = y[j];
+      }
+      if (e.stats_out) {
+        int nv = min(32, max(0, e.n_valid - n0));
+        if (nv > 0) {
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += (j < nv) ? y[j] : 0.f;
+          float m = s / (float)nv;
+          float q2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float d = (j < nv) ? (y[j] - m) : 0.f;
+            q2 += d * d;
+          }
+          stats_merge(sn, smean, sm2, (float)nv, m, q2);
+        }
+      }
+    }
+    if (e.stats_out) e.stats_out[((size_t)rt * n_tiles + nt) * TILE_M + r] = make_float2(smean, sm2);
+  } else if constexpr (EPI == EPI_MODLN) {
+    // merge LayerNorm partials of h for this row
+    float sn = 0.f, mean = 0.f, m2 = 0.f;
+    for (int p = 0; p < e.stats_nt; ++p) {
+      float2 s = e.stats_in[((size_t)rt * e.stats_nt + p) * TILE_M + r];
+      float nb = (float)min(TILE_N, e.h_dim - p * TILE_N);
+      stats_merge(sn, mean, m2, nb, s.x, s.y);
+    }
+    const float rstd = rsqrtf(m2 / (float)e.h_dim + 1e-5f);
+    __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + nt) * TILE_ELEMS;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw2[32];
+      tmem_ld32(tmem_tile + c * 32, raw);        // scale cols
+      tmem_ld32(tmem_tile + 64 + c * 32, raw2);  // shift cols
+      tmem_ld_wait();
+      const int hc0 = nt * 64 + c * 32;          // hidden column of y[0]
+      const float* bs = e.bias + nt * TILE_N + c * 32;
+      float y[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 hv = e.h_tiled[((size_t)rt * e.h_ld4 + (hc0 >> 2) + q) * TILE_M + r];
+        float hx[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int j = q * 4 + i;
+          float scale = __uint_as_float(raw[j]) + __ldg(bs + j);
+          float shift = __uint_as_float(raw2[j]) + __ldg(bs + 64 + j);
+          float xn = (hx[i] - mean) * rstd;
+          y[j] = (hc0 + j < e.h_dim) ? fmaf(xn, 1.0f + scale, shift) : 0.f;
+        }
+      }
+      store_packed32(tile, r, c * 32, y);
+    }
+  } else {  // EPI_SCORE
+    const float mult = __ldg(e.out_mult);
+    const float tw = e.tw_rows ? ((row < e.rows_valid) ? __ldg(e.tw_rows + row) : 0.f) : e.tw_scalar;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int n0 = nt * TILE_N + c * 32;
+      if (n0 >= e.n_valid && !e.out_packed) break;
+      tmem_ld32(tmem_tile + c * 32, raw);
+      tmem_ld_wait();
+      float y[32];
+      const bool live = row < e.rows_valid;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float s = fminf(fmaxf(__uint_as_float(raw[j]), -10.f), 10.f);
+        s = __fmul_rn(s, mult);
+        if (e.tw_rows || e.tw_scalar != 1.0f) s = __fmul_rn(s, tw);
+        y[j] = s;
+      }
+      if (e.do_step) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int col = n0 + q * 4;
+          float4 zv = make_float4(0.f, 0.f, 0.f, 0.f), ev = zv;
+          const bool ok = live && (col + 3 < e.n_valid);
+          if (ok) {
+            zv = *reinterpret_cast<const float4*>(e.z_in + (size_t)row * e.n_valid + col);
+            if (e.eps) ev = *reinterpret_cast<const float4*>(e.eps + (size_t)row * e.n_valid + col);
+          }
+          float zz[4] = {zv.x, zv.y, zv.z, zv.w}, ee[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            // (z + s1*score) * ra ; c1*pred + c2*z ; + sigma*eps   (rounding order of the reference)
+            float pred = __fmul_rn(__fadd_rn(zz[i], __fmul_rn(e.c_s1, y[q * 4 + i])), e.c_ra);
+            float mu = __fadd_rn(__fmul_rn(e.c_c1, pred), __fmul_rn(e.c_c2, zz[i]));
+            if (e.eps) mu = __fadd_rn(mu, __fmul_rn(e.c_sigma, ee[i]));
+            y[q * 4 + i] = ok ? mu : 0.f;
+          }
+          if (ok)
+            *reinterpret_cast<float4*>(e.z_out + (size_t)row * e.n_valid + col) =
+                make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+        }
+        if (e.out_packed && (n0 >> 6) < e.out_kb) {
+          __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + (n0 >> 6)) * TILE_ELEMS;
+          store_packed32(tile, r, n0 & 63, y);
+        }
+      } else if (live) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int col = n0 + q * 4;
+          if (col + 3 < e.n_valid)
+            *reinterpret_cast<float4*>(e.z_out + (size_t)row * e.n_valid + col) =
+                make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared-memory control block
+struct alignas(8) GemmCtrl {
+  uint64_t ring_full[MAX_RING];
+  uint64_t ring_empty[MAX_RING];
+  uint64_t a_full[MAX_RES_KB];
+  uint64_t a_empty[MAX_RES_KB];
+  uint64_t acc_full[4];
+  uint64_t acc_empty[4];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(GemmCtrl) <= SMEM_CTRL, "control block too large");
+
+// G   : n-tiles accumulated concurrently per unit (1, 2 or 4); they share each A k-block.
+// RES : A row tile resident in shared memory (kb <= MAX_RES_KB) vs streamed through the ring.
+template <int EPI, int G, bool RES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  GemmCtrl* ctrl = reinterpret_cast<GemmCtrl*>(smem);
+  const uint32_t a_smem = base + SMEM_CTRL;                                  // RES: kb tiles
+  const uint32_t ring_smem = a_smem + (RES ? ga.kb * TILE_BYTES : 0);        // ring_stages tiles
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int groups = ga.n_tiles / G;  // units per row tile
+  const int num_units = ga.row_tiles * groups;
+  const int u_begin = (int)((long long)blockIdx.x * num_units / gridDim.x);
+  const int u_end = (int)((long long)(blockIdx.x + 1) * num_units / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_RING; ++i) {
+      mbar_init(smem_u32(&ctrl->ring_full[i]), 1);
+      mbar_init(smem_u32(&ctrl->ring_empty[i]), 1);
+    }
+    for (int i = 0; i < MAX_RES_KB; ++i) {
+      mbar_init(smem_u32(&ctrl->a_full[i]), 1);
+      mbar_init(smem_u32(&ctrl->a_empty[i]), 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(smem_u32(&ctrl->acc_full[i]), 1);
+      mbar_init(smem_u32(&ctrl->acc_empty[i]), 4);  // one arrive per epilogue warp of a group
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&ctrl->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t a_par = 0;
+      int prev_rt = -1;
+      for (int u = u_begin; u < u_end; ++u) {
+        const int rt = u / groups, ng = u % groups;
+        const bool new_rt = RES && (rt != prev_rt);
+        for (int kb = 0; kb < ga.kb; ++kb) {
+          if (RES) {
+            if (new_rt) {
+              const uint32_t fb = smem_u32(&ctrl->a_full[kb]);
+              mbar_wait(smem_u32(&ctrl->a_empty[kb]), a_par ^ 1, ga.err, 1);
+              mbar_arrive_expect_tx(fb, TILE_BYTES);
+              bulk_g2s(a_smem + kb * TILE_BYTES,
+                       ga.A + ((size_t)rt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
+            }
+          } else {
+            const uint32_t fb = smem_u32(&ctrl->ring_full[stage]);
+            mbar_wait(smem_u32(&ctrl->ring_empty[stage]), phase ^ 1, ga.err, 2);
+            mbar_arrive_expect_tx(fb, TILE_BYTES);
+            bulk_g2s(ring_smem + stage * TILE_BYTES,
+                     ga.A + ((size_t)rt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
+            if (++stage == ring_stages) { stage = 0; phase ^= 1; }
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const int nt = ng * G + g;
+            const uint32_t fb = smem_u32(&ctrl->ring_full[stage]);
+            mbar_wait(smem_u32(&ctrl->ring_empty[stage]), phase ^ 1, ga.err, 3);
+            mbar_arrive_expect_tx(fb, TILE_BYTES);
+            bulk_g2s(ring_smem + stage * TILE_BYTES,
+                     ga.B + ((size_t)nt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
+            if (++stage == ring_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (new_rt) { a_par ^= 1; prev_rt = rt; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t a_par = 0;
+      int prev_rt = -1;
+      int q = 0;  // 128-col tile sequence number
+      for (int u = u_begin; u < u_end; ++u) {
+        const int rt = u / groups;
+        const bool new_rt = RES && (rt != prev_rt);
+        const bool last_of_rt = RES && (u + 1 == u_end || (u + 1) / groups != rt);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int buf = (q + g) & 3, use = (q + g) >> 2;
+          mbar_wait(smem_u32(&ctrl->acc_empty[buf]), (use & 1) ^ 1, ga.err, 4);
+        }
+        tc_fence_after();
+        for (int kb = 0; kb < ga.kb; ++kb) {
+          uint32_t a_tile;
+          int a_stage = -1;
+          if (RES) {
+            if (new_rt) mbar_wait(smem_u32(&ctrl->a_full[kb]), a_par, ga.err, 5);
+            a_tile = a_smem + kb * TILE_BYTES;
+          } else {
+            mbar_wait(smem_u32(&ctrl->ring_full[stage]), phase, ga.err, 6);
+            a_tile = ring_smem + stage * TILE_BYTES;
+            a_stage = stage;
+            if (++stage == ring_stages) { stage = 0; phase ^= 1; }
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            mbar_wait(smem_u32(&ctrl->ring_full[stage]), phase, ga.err, 7);
+            tc_fence_after();
+            const uint32_t b_tile = ring_smem + stage * TILE_BYTES;
+            const uint32_t d = tmem_base + (uint32_t)(((q + g) & 3) * TILE_N);
+#pragma unroll
+            for (int k = 0; k < TILE_K / 16; ++k) {
+              umma_bf16(d, umma_desc_sw128(a_tile + k * 32), umma_desc_sw128(b_tile + k * 32), idesc,
+                        (kb | k) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&ctrl->ring_empty[stage]));
+            if (++stage == ring_stages) { stage = 0; phase ^= 1; }
+          }
+          if (!RES) umma_commit(smem_u32(&ctrl->ring_empty[a_stage]));
+          if (last_of_rt) umma_commit(smem_u32(&ctrl->a_empty[kb]));
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) umma_commit(smem_u32(&ctrl->acc_full[(q + g) & 3]));
+        q += G;
+        if (new_rt) { a_par ^= 1; prev_rt = rt; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (two groups of 4 warps) =====================
+    const int eg = (warp - 4) >> 2;     // group 0/1 handles tile sequence numbers of that parity
+    const int lq = warp & 3;            // TMEM lane quadrant this warp may access
+    const int r = lq * 32 + lane;
+    int q = 0;
+    for (int u = u_begin; u < u_end; ++u) {
+      const int rt = u / groups, ng = u % groups;
+#pragma unroll
+      for (int g = 0; g < G; ++g, ++q) {
+        if ((q & 1) != eg) continue;
+        const int buf = q & 3, use = q >> 2;
+        mbar_wait(smem_u32(&ctrl->acc_full[buf]), use & 1, ga.err, 8);
+        tc_fence_after();
+        const uint32_t t = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
+        epilogue_tile<EPI>(ea, t, rt, ng * G + g, ga.n_tiles, r);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&ctrl->acc_empty[buf]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace aid

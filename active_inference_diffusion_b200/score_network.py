@@ -1,0 +1,181 @@
+"""Drop-in `LatentScoreNetwork` whose forward runs on the sm_100a library.
+
+Mirrors the reference's constructor signature, parameter registration order, initialisation
+calls and `state_dict` keys (models/score_networks.py:12-99, 174-212, 238-255, 273-281) so that
+(a) the same `torch.manual_seed` produces identical weights and (b) reference checkpoints load
+unchanged.  The submodules are parameter containers only: `forward` packs the parameters into
+tcgen05 operand tiles (a derived cache, rebuilt when any parameter changes) and calls
+`aid_score_forward`.
+"""
+from __future__ import annotations
+
+import ctypes
+import warnings
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class SinusoidalPositionEmbeddings(nn.Module):
+    """Holds the learnable `freq_scale` (models/score_networks.py:273-281); the embedding itself
+    is computed by `k_sincos_pack` on the device."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.dim = dim
+        self.freq_scale = nn.Parameter(torch.ones(1))
+
+
+class AdaptiveLayerNorm(nn.Module):
+    """adaLN parameters (models/score_networks.py:238-255): zero-initialised modulation."""
+
+    def __init__(self, hidden_dim: int):
+        super().__init__()
+        self.norm = nn.LayerNorm(hidden_dim, elementwise_affine=False)
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_dim, 2 * hidden_dim))
+        nn.init.zeros_(self.adaLN_modulation[1].weight)
+        nn.init.zeros_(self.adaLN_modulation[1].bias)
+
+
+class DiTBlock(nn.Module):
+    """Parameters of one DiT block (models/score_networks.py:174-212)."""
+
+    def __init__(self, hidden_dim: int, num_heads: int, mlp_ratio: float = 4.0):
+        super().__init__()
+        self.hidden_dim = hidden_dim
+        self.num_heads = num_heads
+        self.norm1 = AdaptiveLayerNorm(hidden_dim)
+        self.norm2 = AdaptiveLayerNorm(hidden_dim)
+        self.attention = nn.MultiheadAttention(embed_dim=hidden_dim, num_heads=num_heads,
+                                               batch_first=True, dropout=0.0)
+        inner = int(hidden_dim * mlp_ratio)
+        self.mlp = nn.Sequential(nn.Linear(hidden_dim, inner), nn.GELU(), nn.Linear(inner, hidden_dim))
+        nn.init.xavier_uniform_(self.mlp[0].weight)
+        nn.init.xavier_uniform_(self.mlp[2].weight)
+        nn.init.zeros_(self.mlp[0].bias)
+        nn.init.zeros_(self.mlp[2].bias)
+
+
+class LatentScoreNetwork(nn.Module):
+    """s_theta(z_t, t, o) — same call surface as the reference (models/score_networks.py:12-171)."""
+
+    _warned_dropout = False
+
+    def __init__(self, latent_dim: int, observation_dim: int, hidden_dim: int = 256,
+                 time_embed_dim: int = 128, num_layers: int = 6, use_attention: bool = True,
+                 output_scale: float = 1e-3):
+        super().__init__()
+        self.latent_dim = latent_dim
+        self.observation_dim = observation_dim
+        self.hidden_dim = hidden_dim
+        self.time_embed_dim = time_embed_dim
+        self.num_heads = 8
+        self.mlp_ratio = 4.0
+        self.use_attention = use_attention
+        self.output_scale = output_scale
+        self.time_embed = nn.Sequential(
+            SinusoidalPositionEmbeddings(time_embed_dim),
+            nn.Linear(time_embed_dim, hidden_dim * 2), nn.SiLU(), nn.Linear(hidden_dim * 2, hidden_dim))
+        self.obs_encoder = nn.Sequential(
+            nn.Linear(observation_dim, hidden_dim), nn.LayerNorm(hidden_dim), nn.SiLU(), nn.Dropout(0.1),
+            nn.Linear(hidden_dim, hidden_dim), nn.LayerNorm(hidden_dim), nn.SiLU(),
+            nn.Linear(hidden_dim, hidden_dim), nn.LayerNorm(hidden_dim))
+        self.continuous_time_embed = nn.Sequential(
+            nn.Linear(1, time_embed_dim), nn.SiLU(), nn.Linear(time_embed_dim, time_embed_dim), nn.SiLU(),
+            nn.Linear(time_embed_dim, hidden_dim))
+        self.time_scale = nn.Parameter(torch.tensor(1.0))
+        self.register_buffer("grad_norm_ema", torch.tensor(1.0))
+        self.grad_norm_decay = 0.999
+        self.latent_proj = nn.Linear(latent_dim, hidden_dim)
+        if use_attention:
+            self.transformer_blocks = nn.ModuleList(
+                [DiTBlock(hidden_dim, self.num_heads, self.mlp_ratio) for _ in range(num_layers)])
+        self.norm_final = AdaptiveLayerNorm(hidden_dim)
+        self.output_proj = nn.Sequential(
+            nn.Linear(hidden_dim, hidden_dim // 2), nn.SiLU(), nn.Linear(hidden_dim // 2, latent_dim, bias=False))
+        self.output_multiplier = nn.Parameter(torch.ones(1) * output_scale)
+        nn.init.zeros_(self.output_proj[-1].weight)
+        # derived caches (not part of the state_dict)
+        self._packed: Optional[torch.Tensor] = None
+        self._packed_key = None
+        self._ws: Optional[torch.Tensor] = None
+
+    # ---- derived cache -------------------------------------------------------------------
+    @property
+    def num_blocks(self) -> int:
+        return len(self.transformer_blocks) if self.use_attention else 0
+
+    def dims(self) -> _lib.AidScoreDims:
+        return _lib.AidScoreDims(self.latent_dim, self.observation_dim, self.hidden_dim,
+                                 self.time_embed_dim, self.num_blocks)
+
+    def _param_table(self):
+        named = dict(self.named_parameters())
+        keys = list(_lib.SCORE_PARAM_KEYS)
+        for i in range(self.num_blocks):
+            keys += [f"transformer_blocks.{i}.{k}" for k in _lib.SCORE_BLOCK_KEYS]
+        return [named[k] for k in keys]
+
+    def packed_weights(self) -> torch.Tensor:
+        """bf16 tcgen05 operand tiles of the current parameters (rebuilt when they change)."""
+        params = self._param_table()
+        dev = _lib.require_cuda(*params)
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is not None and self._packed_key == key and self._packed.device == dev:
+            return self._packed
+        l = _lib.lib()
+        d = self.dims()
+        nbytes = l.aid_score_packed_bytes(ctypes.byref(d))
+        if nbytes == 0:
+            _lib.check(-1, "aid_score_packed_bytes")
+        keep = [_lib.f32c(p.detach()) for p in params]
+        table = (ctypes.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(l.aid_score_pack(ctypes.byref(d), table, len(keep), packed.data_ptr(), nbytes,
+                                    _lib.stream_ptr(dev)), "aid_score_pack")
+        self._packed, self._packed_key = packed, key
+        return packed
+
+    def workspace(self, batch: int, table_rows: int, device: torch.device) -> torch.Tensor:
+        l = _lib.lib()
+        d = self.dims()
+        need = l.aid_score_workspace_bytes(ctypes.byref(d), batch, table_rows)
+        if need == 0:
+            _lib.check(-1, "aid_score_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    # ---- forward -------------------------------------------------------------------------
+    def forward(self, z_t: torch.Tensor, time: torch.Tensor,
+                observation: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Score [B, L].  The continuous/discrete branch is decided per BATCH from `time`
+        exactly as the reference does (models/score_networks.py:121) — one host sync, as there."""
+        if self.training and observation is not None and not LatentScoreNetwork._warned_dropout:
+            # Parity contract: the fused path evaluates obs_encoder's Dropout(0.1) as the
+            # identity; the reference's train()-mode masks come from a fused native op and cannot be
+            # injected.  Warn once instead of failing so agents that call .train() keep working.
+            warnings.warn("LatentScoreNetwork (b200): obs_encoder Dropout(0.1) is evaluated as identity "
+                          "in train() mode")
+            LatentScoreNetwork._warned_dropout = True
+        if not self.use_attention:
+            raise NotImplementedError("use_attention=False is never instantiated by the reference")
+        dev = _lib.require_cuda(z_t, time, observation)
+        if torch.is_grad_enabled() and (z_t.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # inference entry point; the training path goes through ops.dsm_loss
+            z_t = z_t.detach()
+        z_t, time, observation = _lib.f32c(z_t), _lib.f32c(time), _lib.f32c(observation)
+        batch = z_t.shape[0]
+        continuous = bool(time.max() <= 1.0 and time.min() >= 0.0)
+        packed = self.packed_weights()
+        ws = self.workspace(batch, batch, dev)
+        out = torch.empty(batch, self.latent_dim, dtype=torch.float32, device=dev)
+        d = self.dims()
+        _lib.check(_lib.lib().aid_score_forward(
+            ctypes.byref(d), packed.data_ptr(), ws.data_ptr(), ws.numel(), z_t.data_ptr(), time.data_ptr(),
+            _lib.ptr(observation), batch, int(continuous), out.data_ptr(), _lib.stream_ptr(dev)),
+            "aid_score_forward")
+        return out

@@ -1,0 +1,129 @@
+/* aid_b200.h — C ABI of libaid_sm100.so: the B200-native (sm_100a) hot path of
+ * neuronphysics/active-inference-diffusion.
+ *
+ * The reference has NO native/FFI layer: its boundary for this path is the
+ * Python nn.Module surface.  Each entry point below names the reference method it replaces;
+ * the Python mirror classes in active_inference_diffusion_b200/ bind these through ctypes
+ * (see INTEGRATION.md for the stub a maintainer would add to the reference itself).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the library never allocates, frees or retains device memory: packed weights and
+ *     workspace are caller-owned buffers whose sizes come from the *_bytes() queries;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), nothing synchronises;
+ *   - return 0 on success, negative on error; aid_last_error() gives the thread-local message;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef AID_B200_H
+#define AID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AID_ABI_VERSION 1
+
+/* LatentScoreNetwork dimensions — models/score_networks.py:20-29 */
+typedef struct AidScoreDims {
+  int32_t latent_dim;     /* L */
+  int32_t obs_dim;        /* O (observation_dim seen by obs_encoder) */
+  int32_t hidden_dim;     /* H, multiple of 64 */
+  int32_t time_embed_dim; /* E, multiple of 64 (reference default 128) */
+  int32_t num_blocks;     /* DiT blocks (reference default 6) */
+} AidScoreDims;
+
+/* Index of each fp32 parameter pointer in the `params` table given to aid_score_pack.
+ * Names are the reference state_dict keys.  Per-block entries start at
+ * AID_SP_BLOCK0 with stride AID_SP_BLOCK_STRIDE. */
+enum AidScoreParam {
+  AID_SP_TIME_SCALE = 0,          /* time_scale                                  [] */
+  AID_SP_OUTPUT_MULTIPLIER,       /* output_multiplier                           [1] */
+  AID_SP_FREQ_SCALE,              /* time_embed.0.freq_scale                     [1] */
+  AID_SP_TE1_W, AID_SP_TE1_B,     /* time_embed.1            [2H,E] [2H] */
+  AID_SP_TE3_W, AID_SP_TE3_B,     /* time_embed.3            [H,2H] [H] */
+  AID_SP_OE0_W, AID_SP_OE0_B,     /* obs_encoder.0           [H,O] [H] */
+  AID_SP_OE1_G, AID_SP_OE1_B,     /* obs_encoder.1 (LayerNorm) [H] [H] */
+  AID_SP_OE4_W, AID_SP_OE4_B,     /* obs_encoder.4           [H,H] [H] */
+  AID_SP_OE5_G, AID_SP_OE5_B,     /* obs_encoder.5 (LayerNorm) */
+  AID_SP_OE7_W, AID_SP_OE7_B,     /* obs_encoder.7           [H,H] [H] */
+  AID_SP_OE8_G, AID_SP_OE8_B,     /* obs_encoder.8 (LayerNorm) */
+  AID_SP_CE0_W, AID_SP_CE0_B,     /* continuous_time_embed.0 [E,1] [E] */
+  AID_SP_CE2_W, AID_SP_CE2_B,     /* continuous_time_embed.2 [E,E] [E] */
+  AID_SP_CE4_W, AID_SP_CE4_B,     /* continuous_time_embed.4 [H,E] [H] */
+  AID_SP_LP_W, AID_SP_LP_B,       /* latent_proj             [H,L] [H] */
+  AID_SP_NF_W, AID_SP_NF_B,       /* norm_final.adaLN_modulation.1 [2H,H] [2H] */
+  AID_SP_OUT0_W, AID_SP_OUT0_B,   /* output_proj.0           [H/2,H] [H/2] */
+  AID_SP_OUT2_W,                  /* output_proj.2.weight    [L,H/2] */
+  AID_SP_BLOCK0                   /* first per-block entry */
+};
+/* per block i: index = AID_SP_BLOCK0 + i*AID_SP_BLOCK_STRIDE + one of: */
+enum AidScoreBlockParam {
+  AID_SPB_N1_W = 0, AID_SPB_N1_B, /* norm1.adaLN_modulation.1 [2H,H] [2H] */
+  AID_SPB_N2_W, AID_SPB_N2_B,     /* norm2.adaLN_modulation.1 */
+  AID_SPB_INPROJ_W, AID_SPB_INPROJ_B, /* attention.in_proj_weight [3H,H], in_proj_bias [3H] */
+  AID_SPB_OUTPROJ_W, AID_SPB_OUTPROJ_B, /* attention.out_proj [H,H] [H] */
+  AID_SPB_FC1_W, AID_SPB_FC1_B,   /* mlp.0 [4H,H] [4H] */
+  AID_SPB_FC2_W, AID_SPB_FC2_B,   /* mlp.2 [H,4H] [H] */
+  AID_SP_BLOCK_STRIDE
+};
+
+int32_t aid_abi_version(void);
+const char* aid_last_error(void);
+/* number of CUDA devices visible; <= 0 means the product path cannot run */
+int32_t aid_device_count(void);
+/* kernels launched by this library on the calling thread since the last reset (bench evidence) */
+int64_t aid_launch_count(void);
+void aid_reset_launch_count(void);
+
+/* ---- weights ------------------------------------------------------------------------------
+ * Derived cache of LatentScoreNetwork parameters: bf16 tcgen05 operand tiles (128x64, 128-byte
+ * swizzle), the single-token attention folded to one HxH matrix, adaLN modulation rows
+ * interleaved per 64 hidden columns, fp32 biases/LayerNorm affine/scalars.
+ * Rebuild whenever the parameters change (optimizer.step / load_state_dict). */
+size_t aid_score_packed_bytes(const AidScoreDims* dims);
+int32_t aid_score_num_params(const AidScoreDims* dims);
+int32_t aid_score_pack(const AidScoreDims* dims, const float* const* params_host_table,
+                       int32_t num_params, void* packed, size_t packed_bytes, void* stream);
+
+/* ---- LatentScoreNetwork.forward — models/score_networks.py:101-171 -------------------------
+ * z_t [B,L], time [B], observation [B,O] or NULL (-> zero embedding :146-149), score_out [B,L],
+ * all fp32 row-major contiguous.  `continuous` is the caller-resolved batch-global branch of
+ * :121 (time.max()<=1 && time.min()>=0). */
+size_t aid_score_workspace_bytes(const AidScoreDims* dims, int32_t batch, int32_t table_rows);
+int32_t aid_score_forward(const AidScoreDims* dims, const void* packed, void* workspace,
+                          size_t workspace_bytes, const float* z_t, const float* time,
+                          const float* observation, int32_t batch, int32_t continuous,
+                          float* score_out, void* stream);
+
+/* ---- reverse diffusion — core/diffusion.py:176-255 and utils/async_collector.py:530-595 -----
+ * Runs `n_steps` denoising steps.  Step s calls the score net with the batch-constant time
+ * step_time_host[s] (T-1..0 as floats for generate_latent_trajectory; step/(T-1) for the
+ * collector loop) and applies p_sample with coefficient index step_index_host[s].
+ * coef_host = 5 arrays of length T, concatenated: sqrt_one_minus_alphas_cumprod,
+ * 1/sqrt(alphas), posterior_mean_coef1, posterior_mean_coef2, sqrt(posterior_variance)
+ * (evaluated by the caller with the same fp32 torch expressions as the reference).
+ * noise: [n_noise, B, L] standard normals in draw order (one per step whose index != 0), or NULL
+ * for deterministic=True.  traj_out (optional): [(n_steps+1), B, L] receives z after every step
+ * (slot 0 = z_init).  z_out [B,L] receives the final latent. */
+int32_t aid_sample(const AidScoreDims* dims, const void* packed, void* workspace,
+                   size_t workspace_bytes, int32_t batch, int32_t n_steps,
+                   const float* step_time_host, const int32_t* step_index_host,
+                   const float* coef_host, int32_t T, const float* observation,
+                   const float* z_init, const float* noise, float* z_out, float* traj_out,
+                   void* stream);
+
+/* ---- primitive exposed for tests: y = act(x W^T + b) through the tcgen05 path --------------
+ * x [M,K], w [N,K], bias [N] or NULL, y [M,N]; act: 0 none, 1 SiLU, 2 ReLU, 3 GELU(erf).
+ * via_packed != 0 routes the result through the bf16 packed epilogue and back (tests EPI_PACK). */
+size_t aid_linear_workspace_bytes(int32_t M, int32_t N, int32_t K);
+int32_t aid_linear(const float* x, const float* w, const float* bias, float* y, int32_t M,
+                   int32_t N, int32_t K, int32_t act, int32_t via_packed, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AID_B200_H */

@@ -1,0 +1,134 @@
+"""CUDA score network and reverse-diffusion sampler vs the oracle restatement (fp32, CPU) on
+identical weights, inputs and injected noise.
+
+Tolerance (bf16 tensor-core operands, fp32 accumulation/LayerNorm/residual):
+  score        rel-L2 <= 1e-2
+  final latent rel-L2 <= 2e-2
+"""
+import pytest
+import torch
+
+from oracle import restatement as R
+from tests.util import gen, make_score_net, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-2
+LATENT_TOL = 2e-2
+
+CONFIGS = [  # L, O, H, NB
+    (64, 17, 128, 2),
+    (32, 17, 128, 2),     # reference CLI dims (examples/train_mujoco.py:150-172): latent 32, hidden 128
+    (128, 17, 512, 6),    # BASELINE config #1/#2 dims
+]
+
+
+@pytest.mark.parametrize("L,O,H,NB", CONFIGS)
+@pytest.mark.parametrize("B", [1, 7, 256])
+def test_score_forward_branches(L, O, H, NB, B):
+    net, params = make_score_net(L, O, H, NB, device="cuda")
+    g = gen(B + L)
+    z = torch.randn(B, L, generator=g)
+    obs = torch.randn(B, O, generator=g)
+    times = {
+        "discrete": torch.full((B,), 7.0),
+        "t1_continuous": torch.full((B,), 1.0),
+        "t0_continuous_x316": torch.zeros(B),
+        "uniform": torch.rand(B, generator=g),
+    }
+    for name, t in times.items():
+        with torch.no_grad():
+            want = R.score_forward(params, z, t, obs)
+            got = net(z.cuda(), t.cuda(), obs.cuda()).cpu()
+        assert torch.isfinite(got).all(), name
+        assert rel_l2(got, want) < SCORE_TOL, (name, rel_l2(got, want))
+
+
+def test_score_forward_no_observation():
+    net, params = make_score_net(64, 17, 128, 2, device="cuda")
+    g = gen(3)
+    z = torch.randn(33, 64, generator=g)
+    t = torch.rand(33, generator=g)
+    with torch.no_grad():
+        want = R.score_forward(params, z, t, None)
+        got = net(z.cuda(), t.cuda(), None).cpu()
+    assert rel_l2(got, want) < SCORE_TOL
+
+
+def test_score_clamp_saturation():
+    net, params = make_score_net(64, 17, 128, 2, device="cuda")
+    with torch.no_grad():
+        net.output_proj[2].weight.mul_(40.0)   # drive pre-clamp scores past +-10
+    params = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    g = gen(4)
+    z = torch.randn(64, 64, generator=g)
+    obs = torch.randn(64, 17, generator=g)
+    t = torch.full((64,), 9.0)
+    with torch.no_grad():
+        want = R.score_forward(params, z, t, obs)
+        got = net(z.cuda(), t.cuda(), obs.cuda()).cpu()
+    sat = (want.abs() >= 10 * 0.1 - 1e-6).float().mean()
+    assert sat > 0.3, sat
+    # saturated entries must be exactly +-10 * multiplier on both sides
+    both = (want.abs() >= 1.0 - 1e-6) & (got.abs() >= 1.0 - 1e-6)
+    assert torch.equal(got[both], want[both])
+    assert (got - want).abs().max() < 0.5
+
+
+@pytest.mark.parametrize("L,O,H,NB,T,sched", [
+    (64, 17, 128, 2, 10, "cosine"),
+    (64, 17, 128, 2, 10, "linear"),
+    (32, 17, 128, 2, 25, "cosine"),
+    (128, 17, 512, 6, 50, "cosine"),
+])
+@pytest.mark.parametrize("B", [7, 256])
+def test_reverse_diffusion(L, O, H, NB, T, sched, B):
+    from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess
+    if H == 512 and B == 256:
+        B = 64   # keep the CPU oracle to a few seconds
+    net, params = make_score_net(L, O, H, NB, device="cuda")
+    diff = LatentDiffusionProcess(DiffusionConfig(num_diffusion_steps=T, beta_schedule=sched), L).cuda()
+    sched_t = R.make_schedule(T, sched)
+    g = gen(T + B)
+    obs = torch.randn(B, O, generator=g)
+    zT = torch.randn(B, L, generator=g)
+    noise = torch.randn(T - 1, B, L, generator=g)
+    with torch.no_grad():
+        want = R.generate_latent_trajectory(params, sched_t, zT, obs, list(noise))
+        got = diff.generate_latent_trajectory(net, B, obs.cuda(), z_init=zT.cuda(), noise=noise.cuda())
+    assert len(got) == T + 1 == len(want)
+    assert torch.equal(got[0].cpu(), zT)
+    for i in (1, T // 2, T - 1, T):
+        e = rel_l2(got[i], want[i])
+        assert e < LATENT_TOL, (i, e)
+
+
+def test_reverse_diffusion_deterministic_and_no_traj():
+    from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess
+    L, O, H, NB, T, B = 64, 17, 128, 2, 8, 19
+    net, params = make_score_net(L, O, H, NB, device="cuda")
+    diff = LatentDiffusionProcess(DiffusionConfig(num_diffusion_steps=T), L).cuda()
+    g = gen(11)
+    obs = torch.randn(B, O, generator=g)
+    zT = torch.randn(B, L, generator=g)
+    with torch.no_grad():
+        want = R.generate_latent_trajectory(params, R.make_schedule(T), zT, obs, [], deterministic=True)
+        got = diff.generate_latent_trajectory(net, B, obs.cuda(), deterministic=True, z_init=zT.cuda(),
+                                              return_trajectory=False)
+    assert len(got) == 2
+    assert rel_l2(got[-1], want[-1]) < LATENT_TOL
+
+
+def test_collector_sampler():
+    from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess
+    L, O, H, NB, T, B, max_steps = 64, 17, 128, 2, 25, 12, 20
+    net, params = make_score_net(L, O, H, NB, device="cuda")
+    diff = LatentDiffusionProcess(DiffusionConfig(num_diffusion_steps=T), L).cuda()
+    g = gen(12)
+    obs = torch.randn(B, O, generator=g)
+    z0 = torch.randn(B, L, generator=g)
+    noise = torch.randn(max_steps - 1, B, L, generator=g)
+    with torch.no_grad():
+        want = R.collector_sample(params, R.make_schedule(T), z0, obs, list(noise), max_steps)
+        got = diff.collector_sample(net, obs.cuda(), max_steps, z_init=z0.cuda(), noise=noise.cuda())
+    assert rel_l2(got, want) < LATENT_TOL, rel_l2(got, want)
