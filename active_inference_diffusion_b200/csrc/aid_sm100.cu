@@ -2,6 +2,7 @@
 // Everything numeric runs in the kernels of gemm.cuh / elementwise.cuh; this file only lays
 // out buffers and enqueues launches on the caller's stream.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -115,20 +116,21 @@ static int pack_linear(const PLin& p, const float* w, const float* b, int mode, 
 
 // ------------------------------------------------------------------------------------------
 // GEMM launch
-template <int EPI, int G, bool RES>
+template <int EPI, int NW, int G, bool RES>
 static int launch_gemm_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t st) {
   static bool configured = false;
-  auto kern = gemm_kernel<EPI, G, RES>;
+  auto kern = gemm_kernel<EPI, NW, G, RES>;
   if (!configured) {
     AID_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
   }
   const int a_bytes = RES ? ga.kb * TILE_BYTES : 0;
-  int ring = (SMEM_LIMIT - 1024 - SMEM_CTRL - a_bytes) / TILE_BYTES;
+  const int slot = NW * TILE_BYTES;
+  int ring = (SMEM_LIMIT - 1024 - SMEM_CTRL - a_bytes) / slot;
   if (ring > MAX_RING) ring = MAX_RING;
-  if (ring < G + 2) return fail("gemm: not enough shared memory for the ring");
-  const size_t smem = 1024 + SMEM_CTRL + a_bytes + (size_t)ring * TILE_BYTES;
-  const int units = ga.row_tiles * (ga.n_tiles / G);
+  if (ring < (RES ? 2 : G + 2)) return fail("gemm: not enough shared memory for the ring");
+  const size_t smem = 1024 + SMEM_CTRL + a_bytes + (size_t)ring * slot;
+  const int units = ga.row_tiles * (ga.n_tiles / (NW * G));
   int grid = units < num_sms() ? units : num_sms();
   if (grid < 1) return 0;
   kern<<<grid, GEMM_THREADS, smem, st>>>(ga, ea, ring);
@@ -146,13 +148,21 @@ static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs e
   ga.kb = w.kb;
   ga.n_tiles = w.n_tiles;
   ga.err = err_flag;
+  static const int dbg = getenv("AID_DEBUG") ? atoi(getenv("AID_DEBUG")) : 0;
+  ga.debug = dbg;
   if (!ea.bias) ea.bias = w.b;
   const bool res = w.kb <= MAX_RES_KB;
-  if (res) return launch_gemm_inst<EPI, 1, true>(ga, ea, st);
-  // streamed A: accumulate as many n-tiles concurrently as TMEM allows so A is read once
-  if (w.n_tiles % 4 == 0) return launch_gemm_inst<EPI, 4, false>(ga, ea, st);
-  if (w.n_tiles % 2 == 0) return launch_gemm_inst<EPI, 2, false>(ga, ea, st);
-  return launch_gemm_inst<EPI, 1, false>(ga, ea, st);
+  const bool wide = (w.n_tiles % 2 == 0) && !(dbg & 4);   // N=256 MMAs whenever the tile count allows
+  if (res) {
+    if (wide) return launch_gemm_inst<EPI, 2, 1, true>(ga, ea, st);
+    return launch_gemm_inst<EPI, 1, 1, true>(ga, ea, st);
+  }
+  // streamed A: accumulate as many columns concurrently as TMEM allows so A is read once
+  if (wide) {
+    if (w.n_tiles % 4 == 0) return launch_gemm_inst<EPI, 2, 2, false>(ga, ea, st);
+    return launch_gemm_inst<EPI, 2, 1, false>(ga, ea, st);
+  }
+  return launch_gemm_inst<EPI, 1, 1, false>(ga, ea, st);
 }
 
 static EpiArgs epi_zero() {

@@ -49,6 +49,7 @@ struct GemmArgs {
   int kb;       // K / 64
   int n_tiles;  // N_pad / 128
   int* err;
+  int debug;    // developer knobs (AID_DEBUG env): 1 = skip epilogue math, 2 = skip B loads
 };
 
 struct EpiArgs {
@@ -88,8 +89,21 @@ __device__ __forceinline__ int packed_off(int r, int c) {  // element offset ins
 }
 
 __device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
+// GELU.  The reference uses the exact erf form (nn.GELU(), models/score_networks.py:199).  The
+// epilogue budget is ~16 issue slots per output element (K=512), erff alone costs ~40, so the hot
+// path evaluates x*Phi(x) with Phi(x) ~= 0.5(1+tanh(sqrt(2/pi)(x+0.044715x^3))) on the MUFU tanh
+// unit: |gelu_tanh - gelu_erf| <= 5e-4 absolute (worst near |x|~2.5), i.e. below the bf16 rounding
+// (2^-9 relative) applied to this output right after.  AID_EXACT_GELU restores erff.
 __device__ __forceinline__ float act_gelu(float x) {
+#ifdef AID_EXACT_GELU
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+#else
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+#endif
 }
 __device__ __forceinline__ float act_apply(float x, int act) {
   switch (act) {
@@ -145,27 +159,83 @@ __device__ __forceinline__ void stats_merge(float& n, float& mean, float& m2, fl
 }
 
 // ------------------------------------------------------------------------------------------
-// Epilogue for one 128x128 accumulator tile.  `tmem_tile` already carries this warp's lane base.
+// Epilogue for one 128x128 accumulator tile, split in two phases so that global-memory latency
+// hides behind the MMAs of the same tile:
+//   epi_prefetch : everything that does NOT depend on the accumulator (residual / h rows,
+//                  LayerNorm partials) is loaded into registers BEFORE waiting on acc_full;
+//   epi_finish   : TMEM -> registers, math, stores.
 // rt/nt: row tile / n-tile indices; r: row inside the tile (== TMEM lane).
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_tile, int rt, int nt,
-                                              int n_tiles, int r) {
+struct EpiPre {};
+template <>
+struct EpiPre<EPI_F32> {
+  float4 res[2][8];  // residual chunks c and c+1 (double buffer)
+};
+template <>
+struct EpiPre<EPI_MODLN> {
+  float4 h[16];      // the 64 hidden columns this tile normalises
+  float mean, rstd;
+};
+
+__device__ __forceinline__ void load_bias32(const float* bias, int n0, float (&b)[32]) {
+  if (bias) {
+    const float4* p = reinterpret_cast<const float4*>(bias + n0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 v = __ldg(p + q);
+      b[q * 4 + 0] = v.x; b[q * 4 + 1] = v.y; b[q * 4 + 2] = v.z; b[q * 4 + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = 0.f;
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_prefetch(const EpiArgs& e, int rt, int nt, int r, EpiPre<EPI>& pre) {
+  if constexpr (EPI == EPI_F32) {
+    if (e.resid_tiled) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          pre.res[c][q] = e.resid_tiled[((size_t)rt * e.ld4 + ((nt * TILE_N + c * 32) >> 2) + q) * TILE_M + r];
+    }
+  } else if constexpr (EPI == EPI_MODLN) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      pre.h[q] = e.h_tiled[((size_t)rt * e.h_ld4 + nt * 16 + q) * TILE_M + r];
+    float sn = 0.f, mean = 0.f, m2 = 0.f;
+    for (int p = 0; p < e.stats_nt; ++p) {
+      float2 s = e.stats_in[((size_t)rt * e.stats_nt + p) * TILE_M + r];
+      stats_merge(sn, mean, m2, (float)min(TILE_N, e.h_dim - p * TILE_N), s.x, s.y);
+    }
+    pre.mean = mean;
+    pre.rstd = rsqrtf(m2 / (float)e.h_dim + 1e-5f);
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile, int rt, int nt,
+                                           int n_tiles, int r, EpiPre<EPI>& pre) {
   const int row = rt * TILE_M + r;
   uint32_t raw[32];
 
   if constexpr (EPI == EPI_PACK) {
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
-      tmem_ld32(tmem_tile + c * 32, raw);
-      tmem_ld_wait();
       const int n0 = nt * TILE_N + c * 32;
       float y[32];
+      load_bias32(e.bias, n0, y);
+      tmem_ld32(tmem_tile + c * 32, raw);
+      tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        y[j] = __uint_as_float(raw[j]) + (e.bias ? __ldg(e.bias + n0 + j) : 0.f);
+      for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
       act_apply32(y, e.act);
+      if (n0 + 32 > e.n_valid) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) y[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
+        for (int j = 0; j < 32; ++j) y[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
+      }
       const int kb_out = n0 >> 6;
       if (kb_out < e.out_kb) {
         __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
@@ -174,20 +244,26 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ti
     }
   } else if constexpr (EPI == EPI_F32) {
     float sn = 0.f, smean = 0.f, sm2 = 0.f;
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < 4; ++c) {
-      tmem_ld32(tmem_tile + c * 32, raw);
-      tmem_ld_wait();
       const int n0 = nt * TILE_N + c * 32;
       float y[32];
+      load_bias32(e.bias, n0, y);
+      tmem_ld32(tmem_tile + c * 32, raw);
+      tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        y[j] = __uint_as_float(raw[j]) + (e.bias ? __ldg(e.bias + n0 + j) : 0.f);
+      for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
       if (e.resid_tiled) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          float4 hv = e.resid_tiled[((size_t)rt * e.ld4 + (n0 >> 2) + q) * TILE_M + r];
+          float4 hv = pre.res[c & 1][q];
           y[q * 4 + 0] += hv.x; y[q * 4 + 1] += hv.y; y[q * 4 + 2] += hv.z; y[q * 4 + 3] += hv.w;
+        }
+        if (c + 2 < 4) {  // refill this buffer with chunk c+2 while chunk c+1 is processed
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            pre.res[c & 1][q] =
+                e.resid_tiled[((size_t)rt * e.ld4 + ((n0 + 64) >> 2) + q) * TILE_M + r];
         }
       }
       act_apply32(y, e.act);
@@ -221,38 +297,44 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ti
     }
     if (e.stats_out) e.stats_out[((size_t)rt * n_tiles + nt) * TILE_M + r] = make_float2(smean, sm2);
   } else if constexpr (EPI == EPI_MODLN) {
-    // merge LayerNorm partials of h for this row
-    float sn = 0.f, mean = 0.f, m2 = 0.f;
-    for (int p = 0; p < e.stats_nt; ++p) {
-      float2 s = e.stats_in[((size_t)rt * e.stats_nt + p) * TILE_M + r];
-      float nb = (float)min(TILE_N, e.h_dim - p * TILE_N);
-      stats_merge(sn, mean, m2, nb, s.x, s.y);
-    }
-    const float rstd = rsqrtf(m2 / (float)e.h_dim + 1e-5f);
+    const float mean = pre.mean, rstd = pre.rstd;
     __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + nt) * TILE_ELEMS;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t raw2[32];
-      tmem_ld32(tmem_tile + c * 32, raw);        // scale cols
-      tmem_ld32(tmem_tile + 64 + c * 32, raw2);  // shift cols
-      tmem_ld_wait();
-      const int hc0 = nt * 64 + c * 32;          // hidden column of y[0]
-      const float* bs = e.bias + nt * TILE_N + c * 32;
-      float y[32];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 hv = e.h_tiled[((size_t)rt * e.h_ld4 + (hc0 >> 2) + q) * TILE_M + r];
-        float hx[4] = {hv.x, hv.y, hv.z, hv.w};
+    for (int c = 0; c < 4; ++c) {                 // 16 hidden columns per iteration
+      uint32_t rs[16], rh[16];
+      const float4* bsp = reinterpret_cast<const float4*>(e.bias + nt * TILE_N + c * 16);       // scale biases
+      const float4* bhp = reinterpret_cast<const float4*>(e.bias + nt * TILE_N + 64 + c * 16);  // shift biases
+      tmem_ld16(tmem_tile + c * 16, rs);          // scale cols
+      tmem_ld16(tmem_tile + 64 + c * 16, rh);     // shift cols
+      tmem_ld_wait();
+      const int hc0 = nt * 64 + c * 16;           // hidden column of y[0]
+      float y[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 hv = pre.h[c * 4 + q];
+        const float4 b1 = __ldg(bsp + q), b2 = __ldg(bhp + q);
+        const float hx[4] = {hv.x, hv.y, hv.z, hv.w};
+        const float bs[4] = {b1.x, b1.y, b1.z, b1.w};
+        const float bh[4] = {b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          int j = q * 4 + i;
-          float scale = __uint_as_float(raw[j]) + __ldg(bs + j);
-          float shift = __uint_as_float(raw2[j]) + __ldg(bs + 64 + j);
-          float xn = (hx[i] - mean) * rstd;
+          const int j = q * 4 + i;
+          const float scale = __uint_as_float(rs[j]) + bs[i];
+          const float shift = __uint_as_float(rh[j]) + bh[i];
+          const float xn = (hx[i] - mean) * rstd;
           y[j] = (hc0 + j < e.h_dim) ? fmaf(xn, 1.0f + scale, shift) : 0.f;
         }
       }
-      store_packed32(tile, r, c * 32, y);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint4 v;
+        v.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
+        v.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
+        v.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
+        v.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
+        const int chunk = c * 2 + q;
+        *reinterpret_cast<uint4*>(tile + r * TILE_K + ((chunk ^ (r & 7)) << 3)) = v;
+      }
     }
   } else {  // EPI_SCORE
     const float mult = __ldg(e.out_mult);
@@ -325,22 +407,30 @@ struct alignas(8) GemmCtrl {
 };
 static_assert(sizeof(GemmCtrl) <= SMEM_CTRL, "control block too large");
 
-// G   : n-tiles accumulated concurrently per unit (1, 2 or 4); they share each A k-block.
+// NW  : 128-col n-tiles covered by ONE tcgen05.mma (1 -> N=128, 2 -> N=256).  N=256 is the
+//       instruction shape that reaches the tensor-pipe rate on one CTA (measured on B200,
+//       scripts/micro/mma_rate.cu: N=128 86 cyc/MMA vs 64 ideal; N=256 128 cyc = ideal; and
+//       switching the destination accumulator between consecutive MMAs costs ~250 cyc).
+// G   : MMA units accumulated concurrently (they share each streamed A k-block).
 // RES : A row tile resident in shared memory (kb <= MAX_RES_KB) vs streamed through the ring.
-template <int EPI, int G, bool RES>
+// A "unit" is TU = NW*G consecutive n-tiles of one row tile; TMEM holds 4/TU units in flight.
+template <int EPI, int NW, int G, bool RES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
+  constexpr int TU = NW * G;
+  constexpr int SLOT_BYTES = NW * TILE_BYTES;
+  static_assert(TU <= 4, "unit does not fit TMEM");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
   GemmCtrl* ctrl = reinterpret_cast<GemmCtrl*>(smem);
   const uint32_t a_smem = base + SMEM_CTRL;                                  // RES: kb tiles
-  const uint32_t ring_smem = a_smem + (RES ? ga.kb * TILE_BYTES : 0);        // ring_stages tiles
+  const uint32_t ring_smem = a_smem + (RES ? ga.kb * TILE_BYTES : 0);        // ring_stages slots
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int groups = ga.n_tiles / G;  // units per row tile
+  const int groups = ga.n_tiles / TU;  // units per row tile
   const int num_units = ga.row_tiles * groups;
   const int u_begin = (int)((long long)blockIdx.x * num_units / gridDim.x);
   const int u_end = (int)((long long)(blockIdx.x + 1) * num_units / gridDim.x);
@@ -392,18 +482,25 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
             const uint32_t fb = smem_u32(&ctrl->ring_full[stage]);
             mbar_wait(smem_u32(&ctrl->ring_empty[stage]), phase ^ 1, ga.err, 2);
             mbar_arrive_expect_tx(fb, TILE_BYTES);
-            bulk_g2s(ring_smem + stage * TILE_BYTES,
+            bulk_g2s(ring_smem + stage * SLOT_BYTES,
                      ga.A + ((size_t)rt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
             if (++stage == ring_stages) { stage = 0; phase ^= 1; }
           }
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            const int nt = ng * G + g;
             const uint32_t fb = smem_u32(&ctrl->ring_full[stage]);
             mbar_wait(smem_u32(&ctrl->ring_empty[stage]), phase ^ 1, ga.err, 3);
-            mbar_arrive_expect_tx(fb, TILE_BYTES);
-            bulk_g2s(ring_smem + stage * TILE_BYTES,
-                     ga.B + ((size_t)nt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
+            if (ga.debug & 2) {
+              mbar_arrive(fb);
+            } else {
+              mbar_arrive_expect_tx(fb, SLOT_BYTES);
+#pragma unroll
+              for (int j = 0; j < NW; ++j) {
+                const int nt = (ng * G + g) * NW + j;
+                bulk_g2s(ring_smem + stage * SLOT_BYTES + j * TILE_BYTES,
+                         ga.B + ((size_t)nt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
+              }
+            }
             if (++stage == ring_stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -413,19 +510,19 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N);
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N * NW);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t a_par = 0;
       int prev_rt = -1;
-      int q = 0;  // 128-col tile sequence number
+      int q = 0;  // 128-col tile sequence number (multiple of TU at unit start)
       for (int u = u_begin; u < u_end; ++u) {
         const int rt = u / groups;
         const bool new_rt = RES && (rt != prev_rt);
         const bool last_of_rt = RES && (u + 1 == u_end || (u + 1) / groups != rt);
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const int buf = (q + g) & 3, use = (q + g) >> 2;
+        for (int t = 0; t < TU; ++t) {
+          const int buf = (q + t) & 3, use = (q + t) >> 2;
           mbar_wait(smem_u32(&ctrl->acc_empty[buf]), (use & 1) ^ 1, ga.err, 4);
         }
         tc_fence_after();
@@ -437,7 +534,7 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
             a_tile = a_smem + kb * TILE_BYTES;
           } else {
             mbar_wait(smem_u32(&ctrl->ring_full[stage]), phase, ga.err, 6);
-            a_tile = ring_smem + stage * TILE_BYTES;
+            a_tile = ring_smem + stage * SLOT_BYTES;
             a_stage = stage;
             if (++stage == ring_stages) { stage = 0; phase ^= 1; }
           }
@@ -445,8 +542,8 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
           for (int g = 0; g < G; ++g) {
             mbar_wait(smem_u32(&ctrl->ring_full[stage]), phase, ga.err, 7);
             tc_fence_after();
-            const uint32_t b_tile = ring_smem + stage * TILE_BYTES;
-            const uint32_t d = tmem_base + (uint32_t)(((q + g) & 3) * TILE_N);
+            const uint32_t b_tile = ring_smem + stage * SLOT_BYTES;
+            const uint32_t d = tmem_base + (uint32_t)(((q + g * NW) & 3) * TILE_N);
 #pragma unroll
             for (int k = 0; k < TILE_K / 16; ++k) {
               umma_bf16(d, umma_desc_sw128(a_tile + k * 32), umma_desc_sw128(b_tile + k * 32), idesc,
@@ -459,8 +556,8 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
           if (last_of_rt) umma_commit(smem_u32(&ctrl->a_empty[kb]));
         }
 #pragma unroll
-        for (int g = 0; g < G; ++g) umma_commit(smem_u32(&ctrl->acc_full[(q + g) & 3]));
-        q += G;
+        for (int t = 0; t < TU; ++t) umma_commit(smem_u32(&ctrl->acc_full[(q + t) & 3]));
+        q += TU;
         if (new_rt) { a_par ^= 1; prev_rt = rt; }
       }
     }
@@ -473,13 +570,15 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
     for (int u = u_begin; u < u_end; ++u) {
       const int rt = u / groups, ng = u % groups;
 #pragma unroll
-      for (int g = 0; g < G; ++g, ++q) {
+      for (int t = 0; t < TU; ++t, ++q) {
         if ((q & 1) != eg) continue;
         const int buf = q & 3, use = q >> 2;
+        EpiPre<EPI> pre;
+        if (!(ga.debug & 1)) epi_prefetch<EPI>(ea, rt, ng * TU + t, r, pre);
         mbar_wait(smem_u32(&ctrl->acc_full[buf]), use & 1, ga.err, 8);
         tc_fence_after();
-        const uint32_t t = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
-        epilogue_tile<EPI>(ea, t, rt, ng * G + g, ga.n_tiles, r);
+        const uint32_t tm = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
+        if (!(ga.debug & 1)) epi_finish<EPI>(ea, tm, rt, ng * TU + t, ga.n_tiles, r, pre);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&ctrl->acc_empty[buf]));

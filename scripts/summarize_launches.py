@@ -1,0 +1,17 @@
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel."""
+import collections, csv, re, sys
+lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
+agg = collections.defaultdict(lambda: [0, 0.0])
+for row in csv.DictReader(lines):
+    name = row["Kernel Name"]
+    v = float(row["Metric Value"].replace(",", ""))
+    unit = row["Metric Unit"]
+    v = v / 1e3 if unit in ("ns", "nsecond") else (v * 1e3 if unit in ("ms", "msecond") else v)
+    m = re.search(r"gemm_kernel<\(int\)(\d), \(int\)(\d), \(int\)(\d), \(bool\)(\d)>", name) or re.search(r"gemm_kernel<(\d), (\d), (\d), (\w+)>", name)
+    key = f"gemm<epi={m.group(1)},NW={m.group(2)},G={m.group(3)},res={m.group(4)}>" if m else name.split("(")[0][-44:]
+    agg[key][0] += 1
+    agg[key][1] += v
+tot = sum(v[1] for v in agg.values())
+print(f"launches {sum(v[0] for v in agg.values())}  total {tot:.1f} us")
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:16]:
+    print(f"{k:46s} n={c:5d} total={t:10.1f}us avg={t / c:8.1f}us share={t / tot * 100:5.1f}%")
