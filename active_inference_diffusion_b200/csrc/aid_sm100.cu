@@ -150,6 +150,11 @@ static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs e
   ga.err = err_flag;
   static const int dbg = getenv("AID_DEBUG") ? atoi(getenv("AID_DEBUG")) : 0;
   ga.debug = dbg;
+  // Consecutive GEMMs of a chain walk the row tiles in opposite directions: the tiles the
+  // previous kernel wrote LAST are the ones this kernel reads FIRST, so they are still in the
+  // 126 MB L2 instead of coming back from HBM (activations of a 65k-row batch exceed L2).
+  static thread_local unsigned flip = 0;
+  ga.reverse = (dbg & 8) ? 0 : (int)(flip++ & 1);
   if (!ea.bias) ea.bias = w.b;
   const bool res = w.kb <= MAX_RES_KB;
   const bool wide = (w.n_tiles % 2 == 0) && !(dbg & 4);   // N=256 MMAs whenever the tile count allows

@@ -31,7 +31,7 @@ constexpr int MAX_RES_KB = 8;                    // A resident up to K = 512
 constexpr int MAX_RING = 14;                     // ring stages (16 KiB each)
 constexpr int GEMM_THREADS = 384;
 constexpr int SMEM_LIMIT = 232448;               // 227 KiB opt-in max per CTA
-constexpr int SMEM_CTRL = 1024;                  // barriers + tmem pointer
+constexpr int SMEM_CTRL = 2048;                  // barriers + tmem pointer + bias stages
 
 enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_GELU = 3 };
 
@@ -49,6 +49,7 @@ struct GemmArgs {
   int kb;       // K / 64
   int n_tiles;  // N_pad / 128
   int* err;
+  int reverse;  // walk the units in descending order (see launch_gemm: L2 reuse between kernels)
   int debug;    // developer knobs (AID_DEBUG env): 1 = skip epilogue math, 2 = skip B loads
 };
 
@@ -158,241 +159,7 @@ __device__ __forceinline__ void stats_merge(float& n, float& mean, float& m2, fl
   n = nt;
 }
 
-// ------------------------------------------------------------------------------------------
-// Epilogue for one 128x128 accumulator tile, split in two phases so that global-memory latency
-// hides behind the MMAs of the same tile:
-//   epi_prefetch : everything that does NOT depend on the accumulator (residual / h rows,
-//                  LayerNorm partials) is loaded into registers BEFORE waiting on acc_full;
-//   epi_finish   : TMEM -> registers, math, stores.
-// rt/nt: row tile / n-tile indices; r: row inside the tile (== TMEM lane).
-template <int EPI>
-struct EpiPre {};
-template <>
-struct EpiPre<EPI_F32> {
-  float4 res[2][8];  // residual chunks c and c+1 (double buffer)
-};
-template <>
-struct EpiPre<EPI_MODLN> {
-  float4 h[16];      // the 64 hidden columns this tile normalises
-  float mean, rstd;
-};
-
-__device__ __forceinline__ void load_bias32(const float* bias, int n0, float (&b)[32]) {
-  if (bias) {
-    const float4* p = reinterpret_cast<const float4*>(bias + n0);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 v = __ldg(p + q);
-      b[q * 4 + 0] = v.x; b[q * 4 + 1] = v.y; b[q * 4 + 2] = v.z; b[q * 4 + 3] = v.w;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) b[j] = 0.f;
-  }
-}
-
-template <int EPI>
-__device__ __forceinline__ void epi_prefetch(const EpiArgs& e, int rt, int nt, int r, EpiPre<EPI>& pre) {
-  if constexpr (EPI == EPI_F32) {
-    if (e.resid_tiled) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          pre.res[c][q] = e.resid_tiled[((size_t)rt * e.ld4 + ((nt * TILE_N + c * 32) >> 2) + q) * TILE_M + r];
-    }
-  } else if constexpr (EPI == EPI_MODLN) {
-#pragma unroll
-    for (int q = 0; q < 16; ++q)
-      pre.h[q] = e.h_tiled[((size_t)rt * e.h_ld4 + nt * 16 + q) * TILE_M + r];
-    float sn = 0.f, mean = 0.f, m2 = 0.f;
-    for (int p = 0; p < e.stats_nt; ++p) {
-      float2 s = e.stats_in[((size_t)rt * e.stats_nt + p) * TILE_M + r];
-      stats_merge(sn, mean, m2, (float)min(TILE_N, e.h_dim - p * TILE_N), s.x, s.y);
-    }
-    pre.mean = mean;
-    pre.rstd = rsqrtf(m2 / (float)e.h_dim + 1e-5f);
-  }
-}
-
-template <int EPI>
-__device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile, int rt, int nt,
-                                           int n_tiles, int r, EpiPre<EPI>& pre) {
-  const int row = rt * TILE_M + r;
-  uint32_t raw[32];
-
-  if constexpr (EPI == EPI_PACK) {
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      const int n0 = nt * TILE_N + c * 32;
-      float y[32];
-      load_bias32(e.bias, n0, y);
-      tmem_ld32(tmem_tile + c * 32, raw);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
-      act_apply32(y, e.act);
-      if (n0 + 32 > e.n_valid) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
-      }
-      const int kb_out = n0 >> 6;
-      if (kb_out < e.out_kb) {
-        __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
-        store_packed32(tile, r, n0 & 63, y);
-      }
-    }
-  } else if constexpr (EPI == EPI_F32) {
-    float sn = 0.f, smean = 0.f, sm2 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int n0 = nt * TILE_N + c * 32;
-      float y[32];
-      load_bias32(e.bias, n0, y);
-      tmem_ld32(tmem_tile + c * 32, raw);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
-      if (e.resid_tiled) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 hv = pre.res[c & 1][q];
-          y[q * 4 + 0] += hv.x; y[q * 4 + 1] += hv.y; y[q * 4 + 2] += hv.z; y[q * 4 + 3] += hv.w;
-        }
-        if (c + 2 < 4) {  // refill this buffer with chunk c+2 while chunk c+1 is processed
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            pre.res[c & 1][q] =
-                e.resid_tiled[((size_t)rt * e.ld4 + ((n0 + 64) >> 2) + q) * TILE_M + r];
-        }
-      }
-      act_apply32(y, e.act);
-      if (e.out_tiled) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          e.out_tiled[((size_t)rt * e.ld4 + (n0 >> 2) + q) * TILE_M + r] =
-              make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
-      }
-      if (e.out_rm && row < e.rows_valid) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + j < e.n_valid) e.out_rm[(size_t)row * e.ld_rm + n0 + j] = y[j];
-      }
-      if (e.stats_out) {
-        int nv = min(32, max(0, e.n_valid - n0));
-        if (nv > 0) {
-          float s = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) s += (j < nv) ? y[j] : 0.f;
-          float m = s / (float)nv;
-          float q2 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float d = (j < nv) ? (y[j] - m) : 0.f;
-            q2 += d * d;
-          }
-          stats_merge(sn, smean, sm2, (float)nv, m, q2);
-        }
-      }
-    }
-    if (e.stats_out) e.stats_out[((size_t)rt * n_tiles + nt) * TILE_M + r] = make_float2(smean, sm2);
-  } else if constexpr (EPI == EPI_MODLN) {
-    const float mean = pre.mean, rstd = pre.rstd;
-    __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + nt) * TILE_ELEMS;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {                 // 16 hidden columns per iteration
-      uint32_t rs[16], rh[16];
-      const float4* bsp = reinterpret_cast<const float4*>(e.bias + nt * TILE_N + c * 16);       // scale biases
-      const float4* bhp = reinterpret_cast<const float4*>(e.bias + nt * TILE_N + 64 + c * 16);  // shift biases
-      tmem_ld16(tmem_tile + c * 16, rs);          // scale cols
-      tmem_ld16(tmem_tile + 64 + c * 16, rh);     // shift cols
-      tmem_ld_wait();
-      const int hc0 = nt * 64 + c * 16;           // hidden column of y[0]
-      float y[16];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 hv = pre.h[c * 4 + q];
-        const float4 b1 = __ldg(bsp + q), b2 = __ldg(bhp + q);
-        const float hx[4] = {hv.x, hv.y, hv.z, hv.w};
-        const float bs[4] = {b1.x, b1.y, b1.z, b1.w};
-        const float bh[4] = {b2.x, b2.y, b2.z, b2.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int j = q * 4 + i;
-          const float scale = __uint_as_float(rs[j]) + bs[i];
-          const float shift = __uint_as_float(rh[j]) + bh[i];
-          const float xn = (hx[i] - mean) * rstd;
-          y[j] = (hc0 + j < e.h_dim) ? fmaf(xn, 1.0f + scale, shift) : 0.f;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        uint4 v;
-        v.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
-        v.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
-        v.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
-        v.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
-        const int chunk = c * 2 + q;
-        *reinterpret_cast<uint4*>(tile + r * TILE_K + ((chunk ^ (r & 7)) << 3)) = v;
-      }
-    }
-  } else {  // EPI_SCORE
-    const float mult = __ldg(e.out_mult);
-    const float tw = e.tw_rows ? ((row < e.rows_valid) ? __ldg(e.tw_rows + row) : 0.f) : e.tw_scalar;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      const int n0 = nt * TILE_N + c * 32;
-      if (n0 >= e.n_valid && !e.out_packed) break;
-      tmem_ld32(tmem_tile + c * 32, raw);
-      tmem_ld_wait();
-      float y[32];
-      const bool live = row < e.rows_valid;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float s = fminf(fmaxf(__uint_as_float(raw[j]), -10.f), 10.f);
-        s = __fmul_rn(s, mult);
-        if (e.tw_rows || e.tw_scalar != 1.0f) s = __fmul_rn(s, tw);
-        y[j] = s;
-      }
-      if (e.do_step) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int col = n0 + q * 4;
-          float4 zv = make_float4(0.f, 0.f, 0.f, 0.f), ev = zv;
-          const bool ok = live && (col + 3 < e.n_valid);
-          if (ok) {
-            zv = *reinterpret_cast<const float4*>(e.z_in + (size_t)row * e.n_valid + col);
-            if (e.eps) ev = *reinterpret_cast<const float4*>(e.eps + (size_t)row * e.n_valid + col);
-          }
-          float zz[4] = {zv.x, zv.y, zv.z, zv.w}, ee[4] = {ev.x, ev.y, ev.z, ev.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            // (z + s1*score) * ra ; c1*pred + c2*z ; + sigma*eps   (rounding order of the reference)
-            float pred = __fmul_rn(__fadd_rn(zz[i], __fmul_rn(e.c_s1, y[q * 4 + i])), e.c_ra);
-            float mu = __fadd_rn(__fmul_rn(e.c_c1, pred), __fmul_rn(e.c_c2, zz[i]));
-            if (e.eps) mu = __fadd_rn(mu, __fmul_rn(e.c_sigma, ee[i]));
-            y[q * 4 + i] = ok ? mu : 0.f;
-          }
-          if (ok)
-            *reinterpret_cast<float4*>(e.z_out + (size_t)row * e.n_valid + col) =
-                make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
-        }
-        if (e.out_packed && (n0 >> 6) < e.out_kb) {
-          __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + (n0 >> 6)) * TILE_ELEMS;
-          store_packed32(tile, r, n0 & 63, y);
-        }
-      } else if (live) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int col = n0 + q * 4;
-          if (col + 3 < e.n_valid)
-            *reinterpret_cast<float4*>(e.z_out + (size_t)row * e.n_valid + col) =
-                make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
-        }
-      }
-    }
-  }
-}
+#include "epilogue.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Shared-memory control block
@@ -404,8 +171,11 @@ struct alignas(8) GemmCtrl {
   uint64_t acc_full[4];
   uint64_t acc_empty[4];
   uint32_t tmem_base;
+  uint32_t pad_[(1024 - (2 * MAX_RING + 2 * MAX_RES_KB + 8) * 8 - 4) / 4];
+  float bias_stage[2][TILE_N];   // per epilogue group; 1024-byte offset
+  uint8_t pad2_[SMEM_CTRL - 1024 - 2 * TILE_N * 4];
 };
-static_assert(sizeof(GemmCtrl) <= SMEM_CTRL, "control block too large");
+static_assert(sizeof(GemmCtrl) == SMEM_CTRL, "control block must be exactly SMEM_CTRL bytes");
 
 // NW  : 128-col n-tiles covered by ONE tcgen05.mma (1 -> N=128, 2 -> N=256).  N=256 is the
 //       instruction shape that reaches the tensor-pipe rate on one CTA (measured on B200,
@@ -467,7 +237,8 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       uint32_t a_par = 0;
       int prev_rt = -1;
       for (int u = u_begin; u < u_end; ++u) {
-        const int rt = u / groups, ng = u % groups;
+        const int ue = ga.reverse ? num_units - 1 - u : u;
+        const int rt = ue / groups, ng = ue % groups;
         const bool new_rt = RES && (rt != prev_rt);
         for (int kb = 0; kb < ga.kb; ++kb) {
           if (RES) {
@@ -517,15 +288,10 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       int prev_rt = -1;
       int q = 0;  // 128-col tile sequence number (multiple of TU at unit start)
       for (int u = u_begin; u < u_end; ++u) {
-        const int rt = u / groups;
+        const int rt = (ga.reverse ? num_units - 1 - u : u) / groups;
         const bool new_rt = RES && (rt != prev_rt);
-        const bool last_of_rt = RES && (u + 1 == u_end || (u + 1) / groups != rt);
-#pragma unroll
-        for (int t = 0; t < TU; ++t) {
-          const int buf = (q + t) & 3, use = (q + t) >> 2;
-          mbar_wait(smem_u32(&ctrl->acc_empty[buf]), (use & 1) ^ 1, ga.err, 4);
-        }
-        tc_fence_after();
+        const bool last_of_rt =
+            RES && (u + 1 == u_end || (ga.reverse ? num_units - 2 - u : u + 1) / groups != rt);
         for (int kb = 0; kb < ga.kb; ++kb) {
           uint32_t a_tile;
           int a_stage = -1;
@@ -540,6 +306,13 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
           }
 #pragma unroll
           for (int g = 0; g < G; ++g) {
+            if (kb == 0) {  // this unit's accumulator slots must have been drained by the epilogue
+#pragma unroll
+              for (int j = 0; j < NW; ++j) {
+                const int sl = q + g * NW + j;
+                mbar_wait(smem_u32(&ctrl->acc_empty[sl & 3]), ((sl >> 2) & 1) ^ 1, ga.err, 4);
+              }
+            }
             mbar_wait(smem_u32(&ctrl->ring_full[stage]), phase, ga.err, 7);
             tc_fence_after();
             const uint32_t b_tile = ring_smem + stage * SLOT_BYTES;
@@ -568,17 +341,19 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
     const int r = lq * 32 + lane;
     int q = 0;
     for (int u = u_begin; u < u_end; ++u) {
-      const int rt = u / groups, ng = u % groups;
+      const int ue = ga.reverse ? num_units - 1 - u : u;
+      const int rt = ue / groups, ng = ue % groups;
 #pragma unroll
       for (int t = 0; t < TU; ++t, ++q) {
         if ((q & 1) != eg) continue;
         const int buf = q & 3, use = q >> 2;
         EpiPre<EPI> pre;
-        if (!(ga.debug & 1)) epi_prefetch<EPI>(ea, rt, ng * TU + t, r, pre);
+        float* sb = ctrl->bias_stage[eg];
+        if (!(ga.debug & 1)) epi_prefetch<EPI>(ea, rt, ng * TU + t, r, sb, 1 + eg, pre);
         mbar_wait(smem_u32(&ctrl->acc_full[buf]), use & 1, ga.err, 8);
         tc_fence_after();
         const uint32_t tm = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
-        if (!(ga.debug & 1)) epi_finish<EPI>(ea, tm, rt, ng * TU + t, ga.n_tiles, r, pre);
+        if (!(ga.debug & 1)) epi_finish<EPI>(ea, tm, rt, ng * TU + t, ga.n_tiles, r, sb, pre);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&ctrl->acc_empty[buf]));
