@@ -5,6 +5,9 @@ reference's own Python call surface.  See DESIGN.md."""
 from .configs import ActiveInferenceConfig, BeliefDynamicsConfig, DiffusionConfig
 from .diffusion import LatentDiffusionProcess
 from .score_network import LatentScoreNetwork
+from .heads import DiffusionConditionedPolicy, LatentDynamicsModel, ValueNetwork
+from .active_inference import DiffusionActiveInference
 
 __all__ = ["ActiveInferenceConfig", "BeliefDynamicsConfig", "DiffusionConfig",
-           "LatentDiffusionProcess", "LatentScoreNetwork"]
+           "LatentDiffusionProcess", "LatentScoreNetwork", "DiffusionConditionedPolicy",
+           "LatentDynamicsModel", "ValueNetwork", "DiffusionActiveInference"]

@@ -21,6 +21,16 @@ class AidScoreDims(ctypes.Structure):
                 ("time_embed_dim", c_int32), ("num_blocks", c_int32)]
 
 
+class AidHeadsDims(ctypes.Structure):
+    _fields_ = [("latent_dim", c_int32), ("action_dim", c_int32), ("hidden_dim", c_int32),
+                ("time_embed_dim", c_int32)]
+
+
+class AidEfeConfig(ctypes.Structure):
+    _fields_ = [("epistemic_weight", c_float), ("pragmatic_weight", c_float),
+                ("consistency_weight", c_float), ("discount_factor", c_float)]
+
+
 # mirrors enum AidScoreParam / AidScoreBlockParam in include/aid_b200.h
 SCORE_PARAM_KEYS = [
     "time_scale", "output_multiplier", "time_embed.0.freq_scale",
@@ -68,6 +78,19 @@ def _declare(l: ctypes.CDLL) -> None:
     l.aid_sample.argtypes = [P(AidScoreDims), c_void_p, c_void_p, c_size_t, c_int32, c_int32,
                              P(c_float), P(c_int32), P(c_float), c_int32, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p]
+    l.aid_heads_packed_bytes.restype = c_size_t
+    l.aid_heads_packed_bytes.argtypes = [P(AidHeadsDims)]
+    l.aid_heads_pack.restype = c_int32
+    l.aid_heads_pack.argtypes = [P(AidHeadsDims), P(c_void_p), c_int32, c_void_p, c_size_t, c_void_p]
+    l.aid_heads_workspace_bytes.restype = c_size_t
+    l.aid_heads_workspace_bytes.argtypes = [P(AidHeadsDims), c_int32]
+    l.aid_efe_rollout.restype = c_int32
+    l.aid_efe_rollout.argtypes = [P(AidHeadsDims), c_void_p, c_void_p, c_size_t, c_int32, c_int32, c_int32,
+                                  P(AidEfeConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    l.aid_head_forward.restype = c_int32
+    l.aid_head_forward.argtypes = [P(AidHeadsDims), c_void_p, c_void_p, c_size_t, c_int32, c_int32,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]
     l.aid_linear_workspace_bytes.restype = c_size_t
     l.aid_linear_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
     l.aid_linear.restype = c_int32

@@ -1,0 +1,378 @@
+"""Drop-in `DiffusionActiveInference` (core/active_inference.py:19-771) for state observations.
+
+Constructor signature, sub-module names/registration order/initialisation and `state_dict` keys
+follow the reference so seeded weights and checkpoints are interchangeable.  The three hot
+methods run on the sm_100a library:
+
+  update_belief_via_diffusion              -> aid_sample           (reverse diffusion)
+  compute_expected_free_energy_diffusion   -> aid_efe_rollout      (policy/dynamics/reward/value rollout)
+  latent_score_network(...)                -> aid_score_forward
+
+`compute_diffusion_elbo` (training) evaluates the same loss as the reference; in this round its
+autograd graph is built from torch ops on the device (see DESIGN.md "training path") — the native
+fwd/bwd kernels are the next row of SURVEY §8.
+
+Pixel observations (ConvDecoder, SpatialAttentionAggregator) are SURVEY §8(f) "next" and raise.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .diffusion import LatentDiffusionProcess
+from .heads import (DiffusionConditionedPolicy, HeadsBundle, LatentDynamicsModel, ValueNetwork,
+                    make_reward_predictor)
+from .score_network import LatentScoreNetwork
+from . import autograd_path
+
+
+class FunctionSpaceEpistemicEstimator(nn.Module):
+    """State-mode MINE epistemic estimator (core/active_inference.py:839-1063), parameters and
+    forward.  The reference forward calls `self.decoder(z)` on an nn.ModuleList, which raises
+    (:953); here the decoder is applied with `decode_observation`'s skip forward (:237-242), the
+    documented shim of SURVEY §8c(1).  Runs with torch ops on the device (not on the sampling
+    hot path; it yields ONE scalar per call for the whole batch, :1050-1053)."""
+
+    def __init__(self, decoder: nn.Module, latent_dim: int, observation_shape, hidden_dim: int = 256,
+                 spatial_aggregator_output_dim: int = 256, is_pixel_observation: bool = True,
+                 device: Union[str, torch.device] = "cuda"):
+        super().__init__()
+        if is_pixel_observation:
+            raise NotImplementedError("pixel-mode epistemic estimator: SURVEY §8(f) 'next'")
+        self.decoder = decoder
+        self.latent_dim = latent_dim
+        self.is_pixel = False
+        self.device = torch.device(device) if isinstance(device, str) else device
+        self.ntk_samples = 4
+        self.perturbation_scale = nn.Parameter(torch.tensor(0.1)).to(self.device)
+        self.state_dim = observation_shape
+        self.feature_extractor = nn.Sequential(nn.Linear(self.state_dim, 128), nn.ReLU(), nn.Linear(128, 256),
+                                               nn.ReLU(), nn.Linear(256, 128))
+        jacobian_dim = 128 * self.ntk_samples
+        self.jacobian_projector = nn.Sequential(nn.Linear(jacobian_dim, 512), nn.LayerNorm(512), nn.ReLU(),
+                                                nn.Dropout(0.1), nn.Linear(512, 256))
+        self.latent_processor = nn.Sequential(nn.Linear(latent_dim, 128), nn.ReLU(), nn.Linear(128, 128))
+        self.mine_network = nn.Sequential(nn.Linear(spatial_aggregator_output_dim + 128, 512), nn.ReLU(),
+                                          nn.Dropout(0.1), nn.Linear(512, 512), nn.ReLU(), nn.Dropout(0.1),
+                                          nn.Linear(512, 1))
+        self.register_buffer("running_mean", torch.tensor(0.0))
+        self.alpha = 0.01
+        self.to(self.device)
+
+    def to(self, device):
+        super().to(device)
+        self.device = device if isinstance(device, torch.device) else torch.device(device)
+        return self
+
+    def _decode(self, z: torch.Tensor) -> torch.Tensor:
+        m = self.decoder
+        h1 = m[0](z)
+        h2 = m[1](h1) + h1
+        return m[3](m[2](h2))
+
+    def compute_jacobian_features(self, z: torch.Tensor) -> torch.Tensor:
+        was_training = self.decoder.training
+        self.decoder.eval()
+        with torch.no_grad():
+            f_z = self._decode(z)
+        eps = self.perturbation_scale
+        feats = []
+        for _ in range(self.ntk_samples):
+            delta = F.normalize(torch.randn_like(z), dim=-1) * eps
+            with torch.no_grad():
+                f_p = self._decode(z + delta)
+            feats.append(self.feature_extractor((f_p - f_z) / eps))
+        if was_training:
+            self.decoder.train()
+        return self.jacobian_projector(torch.cat(feats, dim=1))
+
+    def forward(self, next_latent_mean: torch.Tensor, next_latent_logvar: torch.Tensor, num_samples: int = 5):
+        B = next_latent_mean.shape[0]
+        zs = [next_latent_mean + torch.randn_like(next_latent_mean) * torch.exp(0.5 * next_latent_logvar)
+              for _ in range(num_samples)]
+        z_all = torch.cat(zs, dim=0)
+        jac = self.compute_jacobian_features(z_all)
+        lat = self.latent_processor(z_all)
+        t_joint = self.mine_network(torch.cat([jac, lat], dim=1))
+        marg = torch.cat([jac[i * B:(i + 1) * B][torch.randperm(B, device=jac.device)]
+                          for i in range(num_samples)], dim=0)
+        t_marg = self.mine_network(torch.cat([marg, lat], dim=1))
+        # ema_loss (:828-836): forward value log(mean(exp(T))), running mean updated on the side
+        t_exp = torch.exp(torch.logsumexp(t_marg, 0) - math.log(t_marg.shape[0])).detach()
+        if float(self.running_mean) == 0:
+            self.running_mean = t_exp.reshape(())
+        else:
+            self.running_mean = (self.alpha * t_exp + (1.0 - self.alpha) * self.running_mean).reshape(())
+        marginal_term = autograd_path.EMALogMeanExp.apply(t_marg, self.running_mean)
+        mi = t_joint.mean() - marginal_term
+        metrics = {"epistemic/mi_estimate": mi.item(), "epistemic/joint_term": t_joint.mean().item(),
+                   "epistemic/marginal_term": marginal_term.item(),
+                   "epistemic/running_mean": float(self.running_mean)}
+        return torch.clamp(mi.expand(B), min=0.0), metrics
+
+
+class DiffusionActiveInference(nn.Module):
+    def __init__(self, observation_dim: int, action_dim: int, latent_dim: int, config,
+                 pixel_shape: Optional[Tuple[int, int, int]] = None):
+        super().__init__()
+        self.observation_dim, self.action_dim, self.latent_dim = observation_dim, action_dim, latent_dim
+        self.config = config
+        self.pixel_shape = pixel_shape
+        self.is_pixel_observation = config.pixel_observation
+        if self.is_pixel_observation:
+            raise NotImplementedError("pixel observations (DrQ-v2 encoder / ConvDecoder) are SURVEY §8(f) 'next'")
+        self.epistemic_dropout_rate = 0.2
+        self.device = torch.device(config.device)
+        self.raw_observation_shape = None
+        self.use_epistemic = True     # b200 switch: False -> epistemic term = 0
+        self._build_models()
+        self.to(self.device)
+        self.current_latent = None
+        self.latent_trajectory = []
+
+    # ---- construction: same order as core/active_inference.py:59-171 -------------------------
+    def _build_models(self) -> None:
+        cfg, H, L = self.config, self.config.hidden_dim, self.latent_dim
+        self.latent_diffusion = LatentDiffusionProcess(cfg.diffusion, latent_dim=L)
+        self.register_buffer("reward_mean", torch.tensor(0.0))
+        self.register_buffer("reward_var", torch.tensor(1.0))
+        self.register_buffer("preference_temperature", torch.tensor(cfg.preference_temperature))
+        # NB the reference hard-codes observation_dim = latent_dim for the score net (:75-80)
+        self.latent_score_network = LatentScoreNetwork(latent_dim=L, observation_dim=L, hidden_dim=H,
+                                                       use_attention=True)
+        self.policy_network = DiffusionConditionedPolicy(latent_dim=L, action_dim=self.action_dim, hidden_dim=H,
+                                                         use_state_dependent_std=True)
+        self.value_network = ValueNetwork(state_dim=L, hidden_dim=H, time_embed_dim=128, num_layers=3)
+        self.latent_dynamics = LatentDynamicsModel(state_dim=L, action_dim=self.action_dim, hidden_dim=H, num_layers=3)
+        p = self.epistemic_dropout_rate
+        self.observation_decoder = nn.ModuleList([
+            nn.Sequential(nn.Linear(L, H * 2), nn.LayerNorm(H * 2), nn.SiLU(), nn.Dropout(p)),
+            nn.Sequential(nn.Linear(H * 2, H * 2), nn.LayerNorm(H * 2), nn.SiLU(), nn.Dropout(p)),
+            nn.Sequential(nn.Linear(H * 2, H), nn.LayerNorm(H), nn.SiLU(), nn.Dropout(p)),
+            nn.Linear(H, self.observation_dim)])
+        self.epistemic_estimator = FunctionSpaceEpistemicEstimator(
+            decoder=self.observation_decoder, latent_dim=L, observation_shape=self.observation_dim, hidden_dim=H,
+            spatial_aggregator_output_dim=cfg.spatial_aggregator_output_dim, is_pixel_observation=False,
+            device=self.device)
+        self.reward_predictor = make_reward_predictor(L, H)
+        self._heads = HeadsBundle(self.policy_network, self.latent_dynamics, self.value_network,
+                                  self.reward_predictor)
+
+    def to(self, device):
+        if isinstance(device, str):
+            device = torch.device(device)
+        super().to(device)
+        self.device = device
+        self.epistemic_estimator.device = device
+        return self
+
+    # ---- small heads ---------------------------------------------------------------------
+    def decode_observation(self, latent: torch.Tensor, decode_to_pixels: bool = True) -> torch.Tensor:
+        latent = latent.to(self.device)
+        m = self.observation_decoder
+        h1 = m[0](latent)
+        h2 = m[1](h1) + h1
+        return m[3](m[2](h2))
+
+    def predict_reward_from_latent(self, latent: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        out = self._heads.head_forward(3, latent.to(self.device))
+        return out[:, 0], torch.exp(torch.clamp(out[:, 1], min=-5, max=2))
+
+    def predict_next_latent(self, latent: torch.Tensor, action: torch.Tensor):
+        latent, action = latent.to(self.device), action.to(self.device)
+        next_mean = latent + self.latent_dynamics(latent, action)      # 2z + f(z,a), SURVEY fact 10
+        return next_mean, torch.full_like(next_mean, float(np.log(0.1)))
+
+    def reparameterize(self, mean: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
+        std = torch.exp(0.5 * logvar)
+        return mean + torch.randn_like(std) * std
+
+    # ---- belief update (core/active_inference.py:256-312) ---------------------------------
+    def update_belief_via_diffusion(self, observation: torch.Tensor,
+                                    raw_observation: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        observation = observation.to(self.device)
+        if observation.dim() == 1:
+            observation = observation.unsqueeze(0)
+        batch_size = observation.shape[0]
+        keep = getattr(self, "keep_trajectory", False)
+        trajectory = self.latent_diffusion.generate_latent_trajectory(
+            score_network=self.latent_score_network, batch_size=batch_size, observation=observation,
+            deterministic=False, return_trajectory=keep)
+        self.current_latent = trajectory[-1]
+        self.latent_trajectory = trajectory
+        if batch_size == 1:
+            latent_mean = self.current_latent.squeeze(0)
+            latent_std = torch.zeros_like(latent_mean)
+        else:
+            latent_mean = self.current_latent.mean(dim=0)
+            latent_std = self.current_latent.std(dim=0)
+        with torch.no_grad():
+            reconstruction_error = F.mse_loss(self.decode_observation(self.current_latent), observation)
+        return {"latent": self.current_latent, "latent_mean": latent_mean, "latent_std": latent_std,
+                "trajectory_length": int(self.config.diffusion.num_diffusion_steps) + 1,
+                "reconstruction_error": reconstruction_error, "observation": observation,
+                "raw_observation": raw_observation}
+
+    # ---- expected free energy (core/active_inference.py:314-396) ----------------------------
+    def compute_expected_free_energy_diffusion(self, latent: torch.Tensor, horizon: int = 5,
+                                               num_trajectories: int = 10, num_ambiguity_samples: int = 10,
+                                               *, policy_noise: Optional[torch.Tensor] = None,
+                                               reparam_noise: Optional[torch.Tensor] = None,
+                                               epistemic: Optional[torch.Tensor] = None):
+        """Keyword-only extensions inject the reference's random draws (parity tests): policy_noise
+        [K*h,B,A] (Normal.rsample), reparam_noise [K*h,B,L]; `epistemic` [K*h] overrides the MINE
+        values.  With `self.use_epistemic` the estimator is evaluated per (k,t) on the rollout's
+        next-latent means exactly as the reference orders it, which needs one extra dynamics pass."""
+        latent = latent.to(self.device)
+        B, K, h = latent.shape[0], num_trajectories, horizon
+        dev = latent.device
+        if policy_noise is None:
+            policy_noise = torch.randn(K * h, B, self.action_dim, device=dev)
+        if reparam_noise is None:
+            reparam_noise = torch.randn(K * h, B, self.latent_dim, device=dev)
+        cfg = {"epistemic_weight": float(self.config.epistemic_weight),
+               "pragmatic_weight": float(self.config.pragmatic_weight),
+               "consistency_weight": float(self.config.consistency_weight),
+               "discount_factor": float(self.config.discount_factor)}
+        metrics: Dict[str, float] = {}
+        if epistemic is None and self.use_epistemic:
+            epistemic, metrics = self._epistemic_sequence(latent, h, K, policy_noise, reparam_noise,
+                                                          num_ambiguity_samples)
+        efe, first_action, prag, cons = self._heads.efe_rollout(
+            latent, h, K, cfg, self.preference_temperature, policy_noise, reparam_noise, epistemic)
+        self.last_first_action = first_action
+        if epistemic is not None:
+            last = epistemic.view(K, h)[:, -1]
+            epi_mean = last.clamp(min=0.0).mean() if epistemic.numel() else torch.zeros((), device=dev)
+        else:
+            epi_mean = torch.zeros((), device=dev)
+        info = {"epistemic_mean": epi_mean, "pragmatic_mean": prag.mean(), "consistency_mean": cons.mean(),
+                "num_trajectories": num_trajectories, "horizon": horizon, **metrics}
+        return efe, info
+
+    def _epistemic_sequence(self, latent, h, K, policy_noise, reparam_noise, num_samples):
+        """MINE value for every (k,t) in rollout order.  The estimator needs the next-latent mean of
+        each step, so the rollout is replayed step by step through the stand-alone head forwards."""
+        vals, metrics = [], {}
+        std = math.exp(0.5 * math.log(0.1))
+        with torch.no_grad():
+            for k in range(K):
+                cur = latent
+                for t in range(h):
+                    d = k * h + t
+                    out = self._heads.head_forward(0, cur)
+                    A = self.action_dim
+                    action = out[:, :A] + torch.exp(torch.clamp(out[:, A:], -20, 2)) * policy_noise[d]
+                    mean, logvar = self.predict_next_latent(cur, action)
+                    e, metrics = self.epistemic_estimator(mean, logvar, num_samples)
+                    vals.append(e[0])
+                    cur = mean + reparam_noise[d] * std
+        return torch.stack(vals), metrics
+
+    def compute_epistemic_value(self, next_latent_mean, next_latent_logvar, num_samples: int = 5):
+        with torch.no_grad():
+            return self.epistemic_estimator(next_latent_mean.to(self.device), next_latent_logvar.to(self.device),
+                                            num_samples)
+
+    # ---- act (core/active_inference.py:478-531) -------------------------------------------
+    def act(self, observation: torch.Tensor, deterministic: bool = False,
+            raw_observation: Optional[torch.Tensor] = None):
+        observation = observation.to(self.device)
+        if observation.dim() == 1:
+            observation = observation.unsqueeze(0)
+        belief = self.update_belief_via_diffusion(observation, raw_observation)
+        latent = belief["latent"]
+        efe, efe_info = self.compute_expected_free_energy_diffusion(latent, horizon=self.config.efe_horizon)
+        action, log_prob, policy_dist = self.policy_network(latent, deterministic=deterministic)
+        # one device->host transfer for all the scalars the reference reads with .item() (:511-528)
+        scalars = torch.stack([efe.mean(), log_prob.mean(), policy_dist.entropy().sum(dim=-1).mean()] +
+                              [v.float().reshape(()) for v in efe_info.values() if torch.is_tensor(v)]).cpu()
+        action = action.cpu()
+        if action.dim() == 2 and action.shape[0] == 1:
+            action = action.squeeze(0)
+        names = [k for k, v in efe_info.items() if torch.is_tensor(v)]
+        info = {**belief, "expected_free_energy": float(scalars[0]), "action_log_prob": float(scalars[1]),
+                "policy_entropy": float(scalars[2]),
+                **{k: v for k, v in efe_info.items() if not torch.is_tensor(v)},
+                **{k: float(scalars[3 + i]) for i, k in enumerate(names)}}
+        return action, info
+
+    # ---- training loss (core/active_inference.py:533-636, 709-771) --------------------------
+    def _compute_latent_kl(self, latent: torch.Tensor, prior_latent: torch.Tensor) -> torch.Tensor:
+        return 0.5 * torch.sum((latent - prior_latent) ** 2, dim=-1)
+
+    def compute_diffusion_elbo(self, observations: torch.Tensor, rewards: torch.Tensor,
+                               latents: Optional[torch.Tensor] = None,
+                               raw_observations: Optional[torch.Tensor] = None, *,
+                               t: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                               prior_eps: Optional[torch.Tensor] = None):
+        """-ELBO as written in the reference (signs included).  Keyword-only `t`,
+        `noise`, `prior_eps` inject the reference's draws (rand / randn_like / randn_like)."""
+        observations, rewards = observations.to(self.device), rewards.to(self.device)
+        B, dev = observations.shape[0], self.device
+        if latents is None:
+            latents = self.update_belief_via_diffusion(observations, raw_observations)["latent"]
+        recon = F.mse_loss(self.decode_observation(latents), observations)
+        if t is None:
+            t = self._importance_sample_time(B, dev) if hasattr(self, "time_importance_weights") \
+                else torch.rand(B, device=dev)
+        if noise is None:
+            noise = torch.randn_like(latents)
+        diff = self.latent_diffusion
+        noisy, _, info_q = diff.continuous_q_sample(latents, t, noise)
+        score_fn = autograd_path.score_forward
+        pred = score_fn(self.latent_score_network, noisy, t, observations)
+        sigma = info_q["sigma"]
+        true_score = -noise / (sigma + 1e-8)
+        w = diff.compute_loss_weight(t)
+        per_sample = w.view(-1) * torch.sum((pred - true_score) ** 2, dim=1)
+        sm = per_sample.mean()
+        gp = self._compute_gradient_penalty(noisy, t, observations)
+        if prior_eps is None:
+            prior = diff.sample_latent_prior(B, dev)
+        else:
+            prior = diff.latent_prior_mean.unsqueeze(0) + torch.exp(diff.latent_prior_log_std).unsqueeze(0) * prior_eps
+        kl = self._compute_latent_kl(latents, prior).mean()
+        klw = torch.exp(-5.0 * t.mean())
+        pr = self.reward_predictor(latents)
+        r_std = torch.exp(torch.clamp(pr[:, 1], min=-5, max=2))
+        rl = -torch.distributions.Normal(pr[:, 0], r_std).log_prob(rewards).mean()
+        c = self.config
+        elbo = -recon + c.kl_weight * kl * klw + c.diffusion_weight * sm + 0.1 * gp - c.reward_weight * rl
+        self._update_time_importance(t, per_sample.detach())
+        vals = torch.stack([recon, kl, sm, elbo, rl, gp, t.mean(), w.mean()]).detach().cpu()   # one D2H
+        keys = ["reconstruction_loss", "kl_loss", "score_matching_loss", "elbo", "reward_loss", "grad_penalty",
+                "mean_time", "loss_weight_mean"]
+        return -elbo, {k: float(v) for k, v in zip(keys, vals)}
+
+    def _compute_gradient_penalty(self, noisy_latents, t, observations) -> torch.Tensor:
+        x = noisy_latents.detach().requires_grad_(True)
+        s = autograd_path.score_forward(self.latent_score_network, x, t, observations)
+        g = torch.autograd.grad(outputs=s.sum(), inputs=x, create_graph=True, retain_graph=True)[0]
+        return torch.mean((g.norm(2, dim=1) - 1.0) ** 2)
+
+    def _importance_sample_time(self, batch_size: int, device: torch.device) -> torch.Tensor:
+        if not hasattr(self, "time_importance_weights"):
+            self.time_importance_weights = torch.ones(100, device=device)
+        probs = F.softmax(self.time_importance_weights, dim=0)
+        idx = torch.multinomial(probs, batch_size, replacement=True)
+        return (idx.float() + torch.rand(batch_size, device=device)) / 100.0
+
+    def _update_time_importance(self, t: torch.Tensor, loss: torch.Tensor) -> None:
+        """Sequential per-sample EMA over 100 bins (:750-771).  The reference does B x 3 host syncs;
+        here the batch is moved to the host once and the same python-float arithmetic is replayed."""
+        if not hasattr(self, "time_importance_weights"):
+            self.time_importance_weights = torch.ones(100, device=t.device)
+        idx = (t * 99).long().clamp(0, 99).cpu().tolist()
+        if loss.dim() > 1:
+            loss = loss.view(loss.shape[0], -1).sum(dim=1)
+        lv = loss.cpu()
+        w = self.time_importance_weights.cpu()
+        for i, b in enumerate(idx):
+            w[b] = 0.99 * w[b].item() + 0.01 * lv[i].item()
+        self.time_importance_weights = w.to(t.device)

@@ -1,6 +1,7 @@
 // libaid_sm100.so — host orchestration and C ABI (see include/aid_b200.h).
 // Everything numeric runs in the kernels of gemm.cuh / elementwise.cuh; this file only lays
 // out buffers and enqueues launches on the caller's stream.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -431,6 +432,7 @@ static int run_obs_encoder(const ScoreW& s, ScoreWS& w, const float* obs, cudaSt
     l.act = (i < 2) ? ACT_SILU : ACT_NONE;
     l.out_packed = (i < 2) ? w.obs_h : nullptr;
     l.out_tiled = (i < 2) ? nullptr : w.obs_emb;
+    l.resid = nullptr;
     k_ln_act<<<dim3(w.RT, ceil_div(H, 64)), 128, 0, st>>>(l);
     AID_LAUNCH_CHECK("k_ln_act");
     a_in = reinterpret_cast<uint8_t*>(w.obs_h);
@@ -686,6 +688,8 @@ extern "C" int32_t aid_linear(const float* x, const float* wt, const float* bias
   }
   return 0;
 }
+
+#include "heads.inc"
 
 // ------------------------------------------------------------------------------------------
 extern "C" int32_t aid_abi_version(void) { return AID_ABI_VERSION; }

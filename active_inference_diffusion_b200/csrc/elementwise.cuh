@@ -252,6 +252,7 @@ struct LnArgs {
   int act;
   __nv_bfloat16* out_packed;  // [rt][ceil(n/64)] or null
   float4* out_tiled;          // [rt][ld4][128] or null
+  const float4* resid;        // tiled [rt][ld4][128], added AFTER the activation, or null
 };
 __global__ void k_ln_act(const LnArgs a) {
   const int rt = blockIdx.x, kb = blockIdx.y, r = threadIdx.x;
@@ -272,12 +273,15 @@ __global__ void k_ln_act(const LnArgs a) {
       float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < a.ld4 * 4) xv = a.x[((size_t)rt * a.ld4 + (c >> 2)) * TILE_M + r];
       float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.resid && c < a.ld4 * 4) rv = a.resid[((size_t)rt * a.ld4 + (c >> 2)) * TILE_M + r];
+      const float rs[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float v = 0.f;
         if (c + i < a.n) {
           v = (xs[i] - mean) * rstd * __ldg(a.gamma + c + i) + __ldg(a.beta + c + i);
-          v = act_apply(v, a.act);
+          v = act_apply(v, a.act) + rs[i];
         }
         y[q * 4 + i] = v;
       }

@@ -126,6 +126,13 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
           e.out_tiled[((size_t)rt * e.ld4 + (n0 >> 2) + q) * TILE_M + r] =
               make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
       }
+      if (e.out_packed && (n0 >> 6) < e.out_kb) {
+        float yp[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) yp[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
+        __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + (n0 >> 6)) * TILE_ELEMS;
+        store_packed32(tile, r, n0 & 63, yp);
+      }
       if (e.out_rm && row < e.rows_valid) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)

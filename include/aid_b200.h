@@ -115,6 +115,74 @@ int32_t aid_sample(const AidScoreDims* dims, const void* packed, void* workspace
                    const float* z_init, const float* noise, float* z_out, float* traj_out,
                    void* stream);
 
+/* ---- EFE heads: policy / dynamics / value / reward -----------------------------------------
+ * DiffusionConditionedPolicy (models/policy_networks.py:12-146, num_layers=3, state-dependent std),
+ * LatentDynamicsModel (models/dynamics_models.py:9-67, num_layers=3), ValueNetwork
+ * (models/value_networks.py:9-60, num_layers=3) and the reward predictor
+ * (core/active_inference.py:160-167) as DiffusionActiveInference builds them (:83-107). */
+typedef struct AidHeadsDims {
+  int32_t latent_dim;      /* L */
+  int32_t action_dim;      /* A */
+  int32_t hidden_dim;      /* H, multiple of 64 */
+  int32_t time_embed_dim;  /* E of ValueNetwork.time_embed (reference: 128), multiple of 64 */
+} AidHeadsDims;
+
+/* fp32 parameter table for aid_heads_pack: state_dict order of policy_network, latent_dynamics,
+ * value_network, reward_predictor (W = weight, B = bias, G = LayerNorm weight). */
+enum AidHeadsParam {
+  AID_HP_PE0_W = 0, AID_HP_PE0_B, AID_HP_PE1_G, AID_HP_PE1_B, AID_HP_PE3_W, AID_HP_PE3_B, /* latent_encoder.{0,1,3} */
+  AID_HP_TR0_W, AID_HP_TR0_B, AID_HP_TR1_G, AID_HP_TR1_B,                                 /* trunk.{0,1} */
+  AID_HP_TR3_W, AID_HP_TR3_B, AID_HP_TR4_G, AID_HP_TR4_B,                                 /* trunk.{3,4} */
+  AID_HP_TR6_W, AID_HP_TR6_B, AID_HP_TR7_G, AID_HP_TR7_B,                                 /* trunk.{6,7} */
+  AID_HP_MH0_W, AID_HP_MH0_B, AID_HP_MH2_W, AID_HP_MH2_B,                                 /* mean_head.{0,2} */
+  AID_HP_LS0_W, AID_HP_LS0_B, AID_HP_LS2_W, AID_HP_LS2_B,                                 /* log_std_head.{0,2} */
+  AID_HP_DY0_W, AID_HP_DY0_B, AID_HP_DY1_G, AID_HP_DY1_B,                                 /* dynamics network.{0,1} */
+  AID_HP_DY3_W, AID_HP_DY3_B, AID_HP_DY4_G, AID_HP_DY4_B,
+  AID_HP_DY6_W, AID_HP_DY6_B, AID_HP_DY7_G, AID_HP_DY7_B,
+  AID_HP_DY9_W, AID_HP_DY9_B,
+  AID_HP_VFREQ, AID_HP_VT1_W, AID_HP_VT1_B,                                               /* value time_embed.{0,1} */
+  AID_HP_V0_W, AID_HP_V0_B, AID_HP_V1_G, AID_HP_V1_B,                                     /* value network.{0,1} */
+  AID_HP_V3_W, AID_HP_V3_B, AID_HP_V4_G, AID_HP_V4_B,
+  AID_HP_V6_W, AID_HP_V6_B, AID_HP_V7_G, AID_HP_V7_B,
+  AID_HP_V9_W, AID_HP_V9_B,
+  AID_HP_R0_W, AID_HP_R0_B, AID_HP_R1_G, AID_HP_R1_B, AID_HP_R3_W, AID_HP_R3_B, AID_HP_R5_W, AID_HP_R5_B, /* reward_predictor.{0,1,3,5} */
+  AID_HP_COUNT
+};
+
+typedef struct AidEfeConfig {   /* configs/config.py:49-54 */
+  float epistemic_weight, pragmatic_weight, consistency_weight, discount_factor;
+} AidEfeConfig;
+
+size_t aid_heads_packed_bytes(const AidHeadsDims* dims);
+int32_t aid_heads_pack(const AidHeadsDims* dims, const float* const* params_host_table,
+                       int32_t num_params, void* packed, size_t packed_bytes, void* stream);
+size_t aid_heads_workspace_bytes(const AidHeadsDims* dims, int32_t batch);
+
+/* compute_expected_free_energy_diffusion — core/active_inference.py:314-396.
+ * For k < num_trajectories, t < horizon (draw index d = k*horizon + t):
+ *   a = policy(z) with rsample noise policy_noise[d] [B,A]; mu' = 2z + f(z,a) (:447-464);
+ *   z' = mu' + reparam_noise[d] * exp(0.5 ln 0.1); prag = pw * r(z')/tau + V(z', t);
+ *   cons = -sum_a H[pi]; G_k += gamma^t (ew * epi[d] + pw * prag + cw * cons); efe = mean_k G_k.
+ * epistemic: device array [K*h] of batch-constant MINE values (the estimator returns one scalar
+ * per call, :1050-1053) or NULL for 0.  preference_temperature: device scalar (module buffer).
+ * Outputs: efe [B]; optional first_action [B,A] (trajectory 0, step 0), pragmatic_last / consistency_last
+ * [K,B] (last-step terms used for the info dict, :381-389). */
+int32_t aid_efe_rollout(const AidHeadsDims* dims, const void* packed, void* workspace,
+                        size_t workspace_bytes, int32_t batch, int32_t horizon,
+                        int32_t num_trajectories, const AidEfeConfig* cfg,
+                        const float* preference_temperature, const float* latent,
+                        const float* policy_noise, const float* reparam_noise,
+                        const float* epistemic, float* efe_out, float* first_action_out,
+                        float* pragmatic_last, float* consistency_last, void* stream);
+
+/* Stand-alone head forwards (called outside the rollout by agents/collector, e.g.
+ * core/active_inference.py:507-510).  which: 0 policy -> out [B,2A] = (mean | raw log_std),
+ * 1 dynamics(z,a) -> out [B,L] = state + net([z,a]) (models/dynamics_models.py:64-67),
+ * 2 value(z,t) -> out [B,1], 3 reward -> out [B,2].  aux = action [B,A] (dynamics) or time [B] (value). */
+int32_t aid_head_forward(const AidHeadsDims* dims, const void* packed, void* workspace,
+                         size_t workspace_bytes, int32_t which, int32_t batch, const float* z,
+                         const float* aux, float* out, void* stream);
+
 /* ---- primitive exposed for tests: y = act(x W^T + b) through the tcgen05 path --------------
  * x [M,K], w [N,K], bias [N] or NULL, y [M,N]; act: 0 none, 1 SiLU, 2 ReLU, 3 GELU(erf).
  * via_packed != 0 routes the result through the bf16 packed epilogue and back (tests EPI_PACK). */

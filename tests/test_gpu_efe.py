@@ -1,0 +1,167 @@
+"""EFE heads, expected-free-energy rollout, belief update and the training loss of the drop-in
+`DiffusionActiveInference` vs the oracle restatement on identical weights and injected noise.
+
+Tolerances: heads/EFE run bf16 operands on tcgen05 -> rel-L2 <= 2e-2 (stated bf16 bound);
+the training loss evaluates in fp32 torch ops on the device -> rel 1e-3 (north_star fp32/TF32 bound).
+"""
+import pytest
+import torch
+
+from oracle import restatement as R
+from oracle.harness import perturb_generic, perturb_state_dict
+from tests.util import gen, rel_l2
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 2e-2
+
+
+def make_ai(L=32, A=6, H=128, T=6, seed=0, device="cuda"):
+    from active_inference_diffusion_b200 import ActiveInferenceConfig, DiffusionActiveInference, DiffusionConfig
+    torch.manual_seed(seed)
+    cfg = ActiveInferenceConfig(hidden_dim=H, latent_dim=L, device="cpu",
+                                diffusion=DiffusionConfig(num_diffusion_steps=T))
+    ai = DiffusionActiveInference(observation_dim=L, action_dim=A, latent_dim=L, config=cfg).eval()
+    ai.latent_score_network.load_state_dict(perturb_state_dict(ai.latent_score_network.state_dict()))
+    for name in ["policy_network", "latent_dynamics", "value_network", "reward_predictor",
+                 "observation_decoder"]:
+        m = getattr(ai, name)
+        m.load_state_dict(perturb_generic(m.state_dict(), 7, 0.05))
+    # only the four learnable tensors of the diffusion process (not the schedule buffers)
+    learn = {k: v for k, v in ai.latent_diffusion.state_dict().items()
+             if k in ("latent_prior_mean", "latent_prior_log_std", "log_snr_min", "log_snr_max")}
+    ai.latent_diffusion.load_state_dict(perturb_generic(learn, 7, 0.05), strict=False)
+    sub = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    nets = dict(policy=sub(ai.policy_network), dynamics=sub(ai.latent_dynamics), value=sub(ai.value_network),
+                reward=sub(ai.reward_predictor), decoder=sub(ai.observation_decoder),
+                score=sub(ai.latent_score_network), diffusion=sub(ai.latent_diffusion),
+                epistemic=sub(ai.epistemic_estimator))
+    return ai.to(device), nets, cfg
+
+
+@pytest.mark.parametrize("L,A,H", [(32, 6, 128), (128, 6, 512), (64, 17, 256)])
+def test_heads_standalone(L, A, H):
+    ai, nets, _ = make_ai(L, A, H)
+    g = gen(1)
+    B = 77
+    z = torch.randn(B, L, generator=g)
+    a = torch.randn(B, A, generator=g)
+    t = torch.full((B,), 3.0)
+    with torch.no_grad():
+        _, _, mean, std = R.policy_forward(nets["policy"], z, None)
+        act, logp, dist = ai.policy_network(z.cuda(), deterministic=True)
+        assert rel_l2(dist.mean, mean) < BF16_TOL
+        assert rel_l2(dist.stddev, std) < BF16_TOL
+        assert torch.equal(act, dist.mean)
+        assert rel_l2(ai.latent_dynamics(z.cuda(), a.cuda()), R.dynamics_forward(nets["dynamics"], z, a)) < BF16_TOL
+        assert rel_l2(ai.value_network(z.cuda(), t.cuda()), R.value_forward(nets["value"], z, t)) < BF16_TOL
+        rm, rs = ai.predict_reward_from_latent(z.cuda())
+        rm2, rs2 = R.reward_head(nets["reward"], z)
+        assert rel_l2(rm, rm2) < BF16_TOL and rel_l2(rs, rs2) < BF16_TOL
+
+
+@pytest.mark.parametrize("L,A,H,B,K,h", [(32, 6, 128, 50, 3, 4), (128, 6, 512, 256, 2, 5), (64, 17, 256, 9, 1, 15)])
+def test_efe_rollout_epistemic_off(L, A, H, B, K, h):
+    ai, nets, cfg = make_ai(L, A, H)
+    ai.use_epistemic = False
+    g = gen(B + K)
+    z = torch.randn(B, L, generator=g)
+    pn = torch.randn(K * h, B, A, generator=g)
+    rn = torch.randn(K * h, B, L, generator=g)
+    noise = [dict(policy=pn[i], reparam=rn[i]) for i in range(K * h)]
+    ecfg = dict(epistemic_weight=cfg.epistemic_weight, pragmatic_weight=cfg.pragmatic_weight,
+                consistency_weight=cfg.consistency_weight, discount_factor=cfg.discount_factor,
+                preference_temperature=float(cfg.preference_temperature))
+    with torch.no_grad():
+        want, winfo, wfirst = R.expected_free_energy(nets, ecfg, z, h, K, noise)
+        got, info = ai.compute_expected_free_energy_diffusion(z.cuda(), horizon=h, num_trajectories=K,
+                                                              policy_noise=pn.cuda(), reparam_noise=rn.cuda())
+    assert got.shape == (B,)
+    assert rel_l2(got, want) < BF16_TOL, rel_l2(got, want)
+    assert rel_l2(ai.last_first_action, wfirst) < BF16_TOL
+    assert abs(float(info["pragmatic_mean"]) - float(winfo["pragmatic_mean"])) < BF16_TOL * (1 + abs(float(winfo["pragmatic_mean"])))
+    assert abs(float(info["consistency_mean"]) - float(winfo["consistency_mean"])) < BF16_TOL * (1 + abs(float(winfo["consistency_mean"])))
+    # argmin over candidates: same index unless the two best candidates are closer than the bf16 bound
+    order = torch.argsort(want)
+    gap = float(want[order[1]] - want[order[0]]) if B > 1 else 1.0
+    if gap > 2 * BF16_TOL * float(want.abs().max()):
+        assert int(torch.argmin(got.cpu())) == int(order[0])
+
+
+def test_efe_rollout_with_supplied_epistemic_scalars():
+    L, A, H, B, K, h = 32, 6, 128, 20, 2, 3
+    ai, nets, cfg = make_ai(L, A, H)
+    g = gen(5)
+    z = torch.randn(B, L, generator=g)
+    pn = torch.randn(K * h, B, A, generator=g)
+    rn = torch.randn(K * h, B, L, generator=g)
+    epi = torch.rand(K * h, generator=g)
+    with torch.no_grad():
+        base, _ = ai.compute_expected_free_energy_diffusion(z.cuda(), h, K, policy_noise=pn.cuda(),
+                                                            reparam_noise=rn.cuda(), epistemic=torch.zeros(K * h).cuda())
+        got, _ = ai.compute_expected_free_energy_diffusion(z.cuda(), h, K, policy_noise=pn.cuda(),
+                                                           reparam_noise=rn.cuda(), epistemic=epi.cuda())
+    # the epistemic term is batch-constant: efe shifts by mean_k sum_t gamma^t * ew * epi[k,t]
+    shift = sum(cfg.discount_factor ** t * cfg.epistemic_weight * float(epi[k * h + t]) for k in range(K) for t in range(h)) / K
+    assert torch.allclose((got - base).cpu(), torch.full((B,), shift), atol=1e-4)
+    assert int(torch.argmin(got)) == int(torch.argmin(base))
+
+
+def test_update_belief_via_diffusion_matches_oracle():
+    L, A, H, T, B = 32, 6, 128, 6, 40
+    ai, nets, _ = make_ai(L, A, H, T)
+    g = gen(9)
+    obs = torch.randn(B, L, generator=g)
+    torch.manual_seed(123)
+    out = ai.update_belief_via_diffusion(obs.cuda())
+    # replay the generator: generate_latent_trajectory draws randn(B,L) then randn(T-1,B,L) on the device
+    torch.manual_seed(123)
+    zT = torch.randn(B, L, device="cuda").cpu()
+    noise = torch.randn(T - 1, B, L, device="cuda").cpu()
+    with torch.no_grad():
+        want = R.generate_latent_trajectory(nets["score"], R.make_schedule(T), zT, obs, list(noise))[-1]
+    assert out["trajectory_length"] == T + 1
+    assert rel_l2(out["latent"], want) < BF16_TOL
+    assert rel_l2(out["latent_mean"], want.mean(0)) < 5e-2
+    with torch.no_grad():
+        rec = torch.nn.functional.mse_loss(R.decode_observation_state(nets["decoder"], want), obs)
+    assert abs(float(out["reconstruction_error"]) - float(rec)) < 2e-2 * float(rec)
+
+
+def test_diffusion_elbo_loss_and_grads_fp32():
+    L, A, H, B = 32, 6, 128, 24
+    ai, nets, cfg = make_ai(L, A, H)
+    g = gen(21)
+    obs = torch.randn(B, L, generator=g)
+    rew = torch.randn(B, generator=g)
+    lat = torch.randn(B, L, generator=g)
+    t = torch.rand(B, generator=g)
+    n1 = torch.randn(B, L, generator=g)
+    n2 = torch.randn(B, L, generator=g)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        loss, info = ai.compute_diffusion_elbo(obs.cuda(), rew.cuda(), lat.cuda(), t=t.cuda(), noise=n1.cuda(),
+                                               prior_eps=n2.cuda())
+        loss.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    sp = {k: v.clone().requires_grad_(True) for k, v in nets["score"].items() if v.is_floating_point()}
+    dp = {k: nets["diffusion"][k].clone().requires_grad_(True)
+          for k in ("latent_prior_mean", "latent_prior_log_std", "log_snr_min", "log_snr_max")}
+    ecfg = dict(kl_weight=cfg.kl_weight, diffusion_weight=cfg.diffusion_weight, reward_weight=cfg.reward_weight)
+    want, winfo, per = R.diffusion_elbo(sp, dp, nets["decoder"], nets["reward"], ecfg, obs, rew, lat, t, n1, n2)
+    want.backward()
+    assert abs(float(loss) - float(want)) < 1e-3 * abs(float(want))
+    for k in ("score_matching_loss", "grad_penalty", "kl_loss", "reward_loss", "reconstruction_loss"):
+        assert abs(info[k] - float(winfo[k])) < 1e-3 * (abs(float(winfo[k])) + 1e-6), k
+    for k, p in ai.latent_score_network.named_parameters():
+        if p.grad is None:
+            continue
+        assert rel_l2(p.grad, sp[k].grad) < 1e-3, (k, rel_l2(p.grad, sp[k].grad))
+    for k, p in ai.latent_diffusion.named_parameters():
+        if p.grad is not None:
+            assert rel_l2(p.grad, dp[k].grad) < 1e-3, k
+    # time-importance bins are integer work: exact
+    w = R.update_time_importance(torch.ones(100), t, per.detach())
+    assert torch.allclose(ai.time_importance_weights.cpu(), w, rtol=1e-3, atol=1e-6)
+    assert torch.equal((t.cuda() * 99).long().clamp(0, 99).cpu(), R.time_importance_bins(t))
