@@ -7,7 +7,8 @@ from .diffusion import LatentDiffusionProcess
 from .score_network import LatentScoreNetwork
 from .heads import DiffusionConditionedPolicy, LatentDynamicsModel, ValueNetwork
 from .active_inference import DiffusionActiveInference
+from .pipeline import CandidateScorer
 
 __all__ = ["ActiveInferenceConfig", "BeliefDynamicsConfig", "DiffusionConfig",
            "LatentDiffusionProcess", "LatentScoreNetwork", "DiffusionConditionedPolicy",
-           "LatentDynamicsModel", "ValueNetwork", "DiffusionActiveInference"]
+           "LatentDynamicsModel", "ValueNetwork", "DiffusionActiveInference", "CandidateScorer"]

@@ -63,6 +63,10 @@ def _declare(l: ctypes.CDLL) -> None:
     l.aid_device_count.restype = c_int32
     l.aid_launch_count.restype = c_int64
     l.aid_reset_launch_count.restype = None
+    l.aid_profile_select.restype = c_int32
+    l.aid_profile_select.argtypes = [c_int32, c_int32, c_int32]
+    l.aid_profile_collect.restype = c_int32
+    l.aid_profile_collect.argtypes = [P(ctypes.c_double), P(c_int64)]
     l.aid_score_packed_bytes.restype = c_size_t
     l.aid_score_packed_bytes.argtypes = [P(AidScoreDims)]
     l.aid_score_num_params.restype = c_int32
@@ -170,3 +174,14 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None, a
     check(l.aid_linear(ptr(x), ptr(w), ptr(b), ptr(y), M, N, K, act, int(via_packed), ptr(ws), ws_bytes,
                        stream_ptr(dev)), "aid_linear")
     return y
+
+
+def profile_select(epi: int, k: int = 0, n: int = 0) -> None:
+    check(lib().aid_profile_select(epi, k, n), "aid_profile_select")
+
+
+def profile_collect():
+    """(total device ms, launches) of the selected GEMM class since the last collect."""
+    ms, n = ctypes.c_double(0.0), c_int64(0)
+    check(lib().aid_profile_collect(ctypes.byref(ms), ctypes.byref(n)), "aid_profile_collect")
+    return ms.value, int(n.value)

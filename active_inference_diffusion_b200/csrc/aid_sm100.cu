@@ -116,6 +116,47 @@ static int pack_linear(const PLin& p, const float* w, const float* b, int mode, 
 }
 
 // ------------------------------------------------------------------------------------------
+// Optional device timing of one GEMM class (bench.py roofline): CUDA events are recorded on the
+// launching stream around every launch whose (epilogue, K blocks, N tiles) match the selection.
+struct GemmProfile {
+  bool on = false;
+  int epi = -1, kb = -1, n_tiles = -1;
+  std::vector<cudaEvent_t> ev;   // start/stop pairs
+  size_t used = 0;
+};
+static GemmProfile g_prof;
+
+extern "C" int32_t aid_profile_select(int32_t epi, int32_t k, int32_t n) {
+  g_prof.on = epi >= 0;
+  g_prof.epi = epi;
+  g_prof.kb = (k + TILE_K - 1) / TILE_K;
+  g_prof.n_tiles = (n + TILE_N - 1) / TILE_N;
+  g_prof.used = 0;
+  return 0;
+}
+extern "C" int32_t aid_profile_collect(double* total_ms, int64_t* launches) {
+  double tot = 0;
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    AID_CHECK(cudaEventSynchronize(g_prof.ev[i + 1]));
+    float ms = 0;
+    AID_CHECK(cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int64_t)(g_prof.used / 2);
+  g_prof.used = 0;
+  return 0;
+}
+static cudaEvent_t prof_event() {
+  if (g_prof.used == g_prof.ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_prof.ev.push_back(e);
+  }
+  return g_prof.ev[g_prof.used++];
+}
+
+// ------------------------------------------------------------------------------------------
 // GEMM launch
 template <int EPI, int NW, int G, bool RES>
 static int launch_gemm_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t st) {
@@ -134,7 +175,11 @@ static int launch_gemm_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t 
   const int units = ga.row_tiles * (ga.n_tiles / (NW * G));
   int grid = units < num_sms() ? units : num_sms();
   if (grid < 1) return 0;
+  const bool prof = g_prof.on && g_prof.epi == EPI && g_prof.kb == ga.kb && g_prof.n_tiles == ga.n_tiles &&
+                    g_prof.used < 200000;
+  if (prof) cudaEventRecord(prof_event(), st);
   kern<<<grid, GEMM_THREADS, smem, st>>>(ga, ea, ring);
+  if (prof) cudaEventRecord(prof_event(), st);
   AID_LAUNCH_CHECK("gemm_kernel");
   return 0;
 }

@@ -1,0 +1,68 @@
+"""`CandidateScorer`: the fused public call of the hot path — observation -> reverse diffusion
+(belief latent) -> expected-free-energy rollout -> (efe, first action) per candidate row.
+
+It composes the two library calls the reference's `act()` makes in sequence
+(core/active_inference.py:492,501) for arbitrary score-net observation width (the reference's
+state agent hard-codes observation_dim = latent_dim) and is the unit that shards
+across ranks: rows are independent, so a rank scores its slice with no collective.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .configs import ActiveInferenceConfig, DiffusionConfig
+from .diffusion import LatentDiffusionProcess
+from .heads import (DiffusionConditionedPolicy, HeadsBundle, LatentDynamicsModel, ValueNetwork,
+                    make_reward_predictor)
+from .score_network import LatentScoreNetwork
+
+
+class CandidateScorer(nn.Module):
+    def __init__(self, observation_dim: int, action_dim: int, config: Optional[ActiveInferenceConfig] = None):
+        super().__init__()
+        self.config = config or ActiveInferenceConfig()
+        c = self.config
+        L, H = c.latent_dim, c.hidden_dim
+        self.observation_dim, self.action_dim, self.latent_dim = observation_dim, action_dim, L
+        self.latent_diffusion = LatentDiffusionProcess(c.diffusion, latent_dim=L)
+        self.register_buffer("preference_temperature", torch.tensor(c.preference_temperature))
+        self.latent_score_network = LatentScoreNetwork(L, observation_dim, H, use_attention=True)
+        self.policy_network = DiffusionConditionedPolicy(L, action_dim, H, use_state_dependent_std=True)
+        self.value_network = ValueNetwork(L, H, time_embed_dim=128, num_layers=3)
+        self.latent_dynamics = LatentDynamicsModel(L, action_dim, H, num_layers=3)
+        self.reward_predictor = make_reward_predictor(L, H)
+        self.heads = HeadsBundle(self.policy_network, self.latent_dynamics, self.value_network, self.reward_predictor)
+
+    def efe_config(self) -> Dict[str, float]:
+        c = self.config
+        return {"epistemic_weight": float(c.epistemic_weight), "pragmatic_weight": float(c.pragmatic_weight),
+                "consistency_weight": float(c.consistency_weight), "discount_factor": float(c.discount_factor)}
+
+    @torch.no_grad()
+    def forward(self, observation: torch.Tensor, horizon: Optional[int] = None, num_trajectories: int = 1,
+                epistemic: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """observation [B,O] (device) -> (efe [B], first_action [B,A], latent [B,L]).
+        All noise (z_T, T-1 step noises, policy and reparameterisation draws) is drawn here on the
+        device, one stream of standard normals per candidate row."""
+        h = int(horizon or self.config.efe_horizon)
+        B, dev = observation.shape[0], observation.device
+        traj = self.latent_diffusion.generate_latent_trajectory(
+            self.latent_score_network, B, observation, deterministic=False, return_trajectory=False)
+        latent = traj[-1]
+        K = int(num_trajectories)
+        policy_noise = torch.randn(K * h, B, self.action_dim, device=dev)
+        reparam_noise = torch.randn(K * h, B, self.latent_dim, device=dev)
+        efe, first_action, _, _ = self.heads.efe_rollout(latent, h, K, self.efe_config(), self.preference_temperature,
+                                                         policy_noise, reparam_noise, epistemic)
+        return efe, first_action, latent
+
+    @torch.no_grad()
+    def select(self, observation: torch.Tensor, **kw) -> Tuple[torch.Tensor, torch.Tensor]:
+        """argmin-EFE candidate (index, action) — new capability (the reference only logs EFE,
+        SURVEY fact 5); index parity vs torch.argmin is exact by construction."""
+        efe, first_action, _ = self.forward(observation, **kw)
+        idx = torch.argmin(efe)
+        return idx, first_action[idx]

@@ -78,6 +78,13 @@ int32_t aid_device_count(void);
 int64_t aid_launch_count(void);
 void aid_reset_launch_count(void);
 
+/* Device timing of one GEMM class for the roofline line of bench.py: while selected, CUDA events
+ * bracket every tcgen05 GEMM launch with this epilogue kind (0 pack, 1 f32/residual, 2 adaLN,
+ * 3 score/step), reduction length k and output width n.  epi < 0 switches it off.
+ * aid_profile_collect synchronises on the recorded events and returns their summed duration. */
+int32_t aid_profile_select(int32_t epi, int32_t k, int32_t n);
+int32_t aid_profile_collect(double* total_ms_host, int64_t* launches_host);
+
 /* ---- weights ------------------------------------------------------------------------------
  * Derived cache of LatentScoreNetwork parameters: bf16 tcgen05 operand tiles (128x64, 128-byte
  * swizzle), the single-token attention folded to one HxH matrix, adaLN modulation rows
