@@ -1,0 +1,115 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the mirror modules keep the reference's state_dict surface, and the product path fails
+loudly without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "aid_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(aid_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from active_inference_diffusion_b200 import _lib
+    lib = _lib.lib()
+    names = header_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"libaid_sm100.so does not export {n}"
+    assert lib.aid_abi_version() == 1
+
+
+def test_size_queries_and_errors_without_gpu():
+    from active_inference_diffusion_b200 import _lib
+    lib = _lib.lib()
+    d = _lib.AidScoreDims(128, 17, 512, 128, 6)
+    assert lib.aid_score_num_params(ctypes.byref(d)) == len(_lib.SCORE_PARAM_KEYS) + 6 * len(_lib.SCORE_BLOCK_KEYS)
+    packed = lib.aid_score_packed_bytes(ctypes.byref(d))
+    # 21.2 M live bf16 parameters (attention folded) ~ 42 MB
+    assert 40e6 < packed < 50e6
+    assert lib.aid_score_workspace_bytes(ctypes.byref(d), 65536, 50) > 5e8
+    bad = _lib.AidScoreDims(128, 17, 500, 128, 6)
+    assert lib.aid_score_packed_bytes(ctypes.byref(bad)) == 0
+    assert b"hidden_dim" in lib.aid_last_error()
+    h = _lib.AidHeadsDims(128, 6, 512, 128)
+    assert lib.aid_heads_packed_bytes(ctypes.byref(h)) > 0
+
+
+def test_no_cpu_fallback():
+    from active_inference_diffusion_b200 import LatentScoreNetwork
+    net = LatentScoreNetwork(32, 17, 64, num_layers=1).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.randn(2, 32), torch.rand(2), torch.randn(2, 17))
+
+
+def test_score_param_table_covers_all_parameters():
+    from active_inference_diffusion_b200 import LatentScoreNetwork, _lib
+    net = LatentScoreNetwork(32, 17, 64, num_layers=2)
+    names = set(dict(net.named_parameters()))
+    table = set(_lib.SCORE_PARAM_KEYS) | {f"transformer_blocks.{i}.{k}" for i in range(2) for k in _lib.SCORE_BLOCK_KEYS}
+    assert table == names
+
+
+def test_state_dict_surface_matches_reference_keys():
+    """Key list recorded from the reference — checkpoints must stay loadable."""
+    from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess, LatentScoreNetwork
+    sd = LatentScoreNetwork(128, 17, 512).state_dict()
+    assert list(sd)[:8] == ["time_scale", "output_multiplier", "grad_norm_ema", "time_embed.0.freq_scale",
+                            "time_embed.1.weight", "time_embed.1.bias", "time_embed.3.weight", "time_embed.3.bias"]
+    assert sd["transformer_blocks.5.attention.in_proj_weight"].shape == (1536, 512)
+    assert sd["output_proj.2.weight"].shape == (128, 256) and "output_proj.2.bias" not in sd
+    assert sum(v.numel() for k, v in sd.items() if k != "grad_norm_ema") == 27238531
+    assert float(sd["output_proj.2.weight"].abs().max()) == 0.0
+    dd = LatentDiffusionProcess(DiffusionConfig(num_diffusion_steps=50), 128).state_dict()
+    assert list(dd) == ["latent_prior_mean", "latent_prior_log_std", "log_snr_min", "log_snr_max", "betas", "alphas",
+                        "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+                        "posterior_variance", "posterior_log_variance_clipped", "loss_weight_cache"]
+
+
+def test_unknown_schedule_raises_like_reference():
+    from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess
+    with pytest.raises(ValueError, match="Unknown schedule"):
+        LatentDiffusionProcess(DiffusionConfig(num_diffusion_steps=10, beta_schedule="sigmoid"), 32)
+
+
+def test_reverse_coefficients_match_oracle_tables():
+    from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess
+    from oracle import restatement as R
+    for sched in ("cosine", "linear"):
+        d = LatentDiffusionProcess(DiffusionConfig(num_diffusion_steps=50, beta_schedule=sched), 128)
+        c = R.reverse_step_coefficients(R.make_schedule(50, sched))
+        got = torch.from_numpy(d.reverse_coefficients())
+        for i, k in enumerate(["sqrt_one_minus_ac", "sqrt_recip_alpha", "coef1", "coef2", "sigma"]):
+            assert torch.equal(got[i], c[k]), (sched, k)
+
+
+def test_active_inference_mirror_seeded_init_checksums():
+    from active_inference_diffusion_b200 import ActiveInferenceConfig, DiffusionActiveInference, DiffusionConfig
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "active_inference_small.pt"), weights_only=False)
+    d = fx["dims"]
+    torch.manual_seed(0)
+    cfg = ActiveInferenceConfig(hidden_dim=d["H"], latent_dim=d["L"], device="cpu",
+                                diffusion=DiffusionConfig(num_diffusion_steps=d["T"]))
+    ai = DiffusionActiveInference(observation_dim=d["L"], action_dim=d["A"], latent_dim=d["L"], config=cfg)
+    sd = ai.state_dict()
+    for k, (s, a) in fx["init_checksums"].items():
+        v = sd[k].double()
+        assert float(v.sum()) == s and float(v.abs().sum()) == a, k
+
+
+def test_shard_bounds_partition():
+    from active_inference_diffusion_b200.distributed import shard_bounds
+    for total in (1, 7, 65536, 262144, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
