@@ -8,7 +8,9 @@ from .score_network import LatentScoreNetwork
 from .heads import DiffusionConditionedPolicy, LatentDynamicsModel, ValueNetwork
 from .active_inference import DiffusionActiveInference
 from .pipeline import CandidateScorer
+from .belief_dynamics import BeliefDynamics, FreeEnergyComputation
 
 __all__ = ["ActiveInferenceConfig", "BeliefDynamicsConfig", "DiffusionConfig",
            "LatentDiffusionProcess", "LatentScoreNetwork", "DiffusionConditionedPolicy",
-           "LatentDynamicsModel", "ValueNetwork", "DiffusionActiveInference", "CandidateScorer"]
+           "LatentDynamicsModel", "ValueNetwork", "DiffusionActiveInference", "CandidateScorer",
+           "BeliefDynamics", "FreeEnergyComputation"]

@@ -95,6 +95,8 @@ def _declare(l: ctypes.CDLL) -> None:
     l.aid_head_forward.restype = c_int32
     l.aid_head_forward.argtypes = [P(AidHeadsDims), c_void_p, c_void_p, c_size_t, c_int32, c_int32,
                                    c_void_p, c_void_p, c_void_p, c_void_p]
+    l.aid_fp_belief_update.restype = c_int32
+    l.aid_fp_belief_update.argtypes = [c_void_p] * 5 + [c_int32, c_int32] + [ctypes.c_double] * 6 + [c_void_p] * 4
     l.aid_linear_workspace_bytes.restype = c_size_t
     l.aid_linear_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
     l.aid_linear.restype = c_int32

@@ -735,6 +735,7 @@ extern "C" int32_t aid_linear(const float* x, const float* wt, const float* bias
 }
 
 #include "heads.inc"
+#include "belief.inc"
 
 // ------------------------------------------------------------------------------------------
 extern "C" int32_t aid_abi_version(void) { return AID_ABI_VERSION; }

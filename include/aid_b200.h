@@ -190,6 +190,18 @@ int32_t aid_head_forward(const AidHeadsDims* dims, const void* packed, void* wor
                          size_t workspace_bytes, int32_t which, int32_t batch, const float* z,
                          const float* aux, float* out, void* stream);
 
+/* ---- BeliefDynamics.update, diagonal covariance — core/belief_dynamics.py:97-172 (fp64) ----
+ * Batched over `rows` independent beliefs, all arrays [rows, latent_dim] float64:
+ *   g = -(mu - o)/ns^2 - mu + s;  mu' = mu - lr*g*dt/(1 + 0.1|g|) + sqrt(2 D dt)*ns*eps;
+ *   v' = clamp(v * exp((2(1/ns^2 + 1) + 2D) dt), max(min_variance,1e-8), max_variance);  p' = 1/v'.
+ * noise may be NULL (eps = 0).  The reference method crashes as shipped; this is
+ * the closed-form restatement for the default Gaussian observation model. */
+int32_t aid_fp_belief_update(const double* mean, const double* variance, const double* observation,
+                             const double* score, const double* noise, int32_t rows, int32_t latent_dim,
+                             double dt, double diffusion_coefficient, double learning_rate,
+                             double noise_scale, double min_variance, double max_variance,
+                             double* mean_out, double* variance_out, double* precision_out, void* stream);
+
 /* ---- primitive exposed for tests: y = act(x W^T + b) through the tcgen05 path --------------
  * x [M,K], w [N,K], bias [N] or NULL, y [M,N]; act: 0 none, 1 SiLU, 2 ReLU, 3 GELU(erf).
  * via_packed != 0 routes the result through the bf16 packed epilogue and back (tests EPI_PACK). */
