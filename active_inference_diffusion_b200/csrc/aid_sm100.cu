@@ -91,7 +91,8 @@ struct PLin {
   const uint8_t* w = nullptr;
   const float* b = nullptr;
   int n = 0, k = 0;        // logical [n, k]
-  int n_tiles = 0, kb = 0; // padded tile counts
+  int n_tiles = 0, kb = 0; // padded tile counts (128-row n-tiles, 64-col k-blocks)
+  int nw = 1;              // packed tile height in n-tiles: 2 -> 256-row tiles for N=256 MMAs
 };
 
 static void plin_shape(PLin& p, int n, int k, bool modln = false) {
@@ -99,6 +100,7 @@ static void plin_shape(PLin& p, int n, int k, bool modln = false) {
   p.k = k;
   p.kb = ceil_div(k, TILE_K);
   p.n_tiles = modln ? ceil_div(n / 2, 64) : ceil_div(n, TILE_N);
+  p.nw = (p.n_tiles % 2 == 0) ? 2 : 1;
 }
 static size_t plin_w_bytes(const PLin& p) { return (size_t)p.n_tiles * p.kb * TILE_BYTES; }
 static size_t plin_b_bytes(const PLin& p) { return (size_t)p.n_tiles * TILE_N * sizeof(float); }
@@ -107,7 +109,7 @@ static int pack_linear(const PLin& p, const float* w, const float* b, int mode, 
   size_t chunks = (size_t)p.n_tiles * p.kb * 1024;
   k_pack_rows<<<ew_grid(chunks), 256, 0, st>>>(
       w, p.n, p.k, p.k, reinterpret_cast<__nv_bfloat16*>(const_cast<uint8_t*>(p.w)), p.n_tiles, p.kb,
-      mode, H);
+      mode, H, p.nw);
   AID_LAUNCH_CHECK("k_pack_rows(weight)");
   int n_pad = p.n_tiles * TILE_N;
   k_pack_bias<<<ceil_div(n_pad, 256), 256, 0, st>>>(b, p.n, const_cast<float*>(p.b), n_pad, mode, H);
@@ -158,10 +160,10 @@ static cudaEvent_t prof_event() {
 
 // ------------------------------------------------------------------------------------------
 // GEMM launch
-template <int EPI, int NW, int G, bool RES>
+template <int EPI, int NW, int G, bool RES, int ACT = ACT_NONE>
 static int launch_gemm_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t st) {
   static bool configured = false;
-  auto kern = gemm_kernel<EPI, NW, G, RES>;
+  auto kern = gemm_kernel<EPI, NW, G, RES, ACT>;
   if (!configured) {
     AID_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
@@ -184,6 +186,16 @@ static int launch_gemm_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t 
   return 0;
 }
 
+template <int EPI, int ACT>
+static int launch_gemm_shape(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t st, bool res, bool wide) {
+  if (res) {
+    if (wide) return launch_gemm_inst<EPI, 2, 1, true, ACT>(ga, ea, st);
+    return launch_gemm_inst<EPI, 1, 1, true, ACT>(ga, ea, st);
+  }
+  if (wide) return launch_gemm_inst<EPI, 2, 1, false, ACT>(ga, ea, st);
+  return launch_gemm_inst<EPI, 1, 1, false, ACT>(ga, ea, st);
+}
+
 template <int EPI>
 static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs ea, cudaStream_t st,
                        int* err_flag) {
@@ -203,17 +215,21 @@ static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs e
   ga.reverse = (dbg & 8) ? 0 : (int)(flip++ & 1);
   if (!ea.bias) ea.bias = w.b;
   const bool res = w.kb <= MAX_RES_KB;
-  const bool wide = (w.n_tiles % 2 == 0) && !(dbg & 4);   // N=256 MMAs whenever the tile count allows
-  if (res) {
-    if (wide) return launch_gemm_inst<EPI, 2, 1, true>(ga, ea, st);
-    return launch_gemm_inst<EPI, 1, 1, true>(ga, ea, st);
+  const bool wide = w.nw == 2;   // N=256 MMAs whenever the tile count allows (fixed at pack time)
+  // A resident in shared memory (K <= 512) or streamed through the ring.  Streamed A: one N=256
+  // unit per pass so TMEM holds two units and the epilogue of unit u overlaps the MMAs of unit u+1
+  // (a 512-column unit fills TMEM and serialises them: 248 us vs 103 us of MMA time for mlp.2 at
+  // 65,536 rows).  The second pass over the same A row tile hits L2.
+  if constexpr (EPI == EPI_PACK || EPI == EPI_F32) {
+    switch (ea.act) {
+      case ACT_SILU: return launch_gemm_shape<EPI, ACT_SILU>(ga, ea, st, res, wide);
+      case ACT_RELU: return launch_gemm_shape<EPI, ACT_RELU>(ga, ea, st, res, wide);
+      case ACT_GELU: return launch_gemm_shape<EPI, ACT_GELU>(ga, ea, st, res, wide);
+      default: return launch_gemm_shape<EPI, ACT_NONE>(ga, ea, st, res, wide);
+    }
+  } else {
+    return launch_gemm_shape<EPI, ACT_NONE>(ga, ea, st, res, wide);
   }
-  // streamed A: accumulate as many columns concurrently as TMEM allows so A is read once
-  if (wide) {
-    if (w.n_tiles % 4 == 0) return launch_gemm_inst<EPI, 2, 2, false>(ga, ea, st);
-    return launch_gemm_inst<EPI, 2, 1, false>(ga, ea, st);
-  }
-  return launch_gemm_inst<EPI, 1, 1, false>(ga, ea, st);
 }
 
 static EpiArgs epi_zero() {
@@ -326,7 +342,8 @@ extern "C" int32_t aid_score_pack(const AidScoreDims* dims, const float* const* 
     size_t chunks = (size_t)b.attn.n_tiles * b.attn.kb * 1024;
     k_pack_folded_attn<<<ew_grid(chunks, 128), 128, 0, st>>>(
         B[AID_SPB_INPROJ_W], B[AID_SPB_OUTPROJ_W], H,
-        reinterpret_cast<__nv_bfloat16*>(const_cast<uint8_t*>(b.attn.w)), b.attn.n_tiles, b.attn.kb);
+        reinterpret_cast<__nv_bfloat16*>(const_cast<uint8_t*>(b.attn.w)), b.attn.n_tiles, b.attn.kb,
+        b.attn.nw);
     AID_LAUNCH_CHECK("k_pack_folded_attn");
     int n_pad = b.attn.n_tiles * TILE_N;
     k_folded_attn_bias<<<ceil_div(n_pad, 128), 128, 0, st>>>(
@@ -461,7 +478,7 @@ static int run_obs_encoder(const ScoreW& s, ScoreWS& w, const float* obs, cudaSt
   }
   const int kbo = ceil_div(s.O, TILE_K);
   k_pack_rows<<<ew_grid((size_t)w.RT * kbo * 1024), 256, 0, st>>>(obs, w.B, s.O, s.O, w.obsp, w.RT, kbo,
-                                                                   MAP_PLAIN, 0);
+                                                                   MAP_PLAIN, 0, 1);
   AID_LAUNCH_CHECK("k_pack_rows(obs)");
   const PLin* lin[3] = {&s.oe0, &s.oe4, &s.oe7};
   const float* g[3] = {s.oe1_g, s.oe5_g, s.oe8_g};
@@ -585,7 +602,7 @@ extern "C" int32_t aid_score_forward(const AidScoreDims* dims, const void* packe
   AID_TRY(run_obs_encoder(s, w, observation, st));
   AID_TRY(run_cond(s, w, continuous != 0, -1, st));
   const int kbl = ceil_div(s.L, TILE_K);
-  k_pack_rows<<<ew_grid((size_t)w.RT * kbl * 1024), 256, 0, st>>>(z_t, batch, s.L, s.L, w.zp, w.RT, kbl, MAP_PLAIN, 0);
+  k_pack_rows<<<ew_grid((size_t)w.RT * kbl * 1024), 256, 0, st>>>(z_t, batch, s.L, s.L, w.zp, w.RT, kbl, MAP_PLAIN, 0, 1);
   AID_LAUNCH_CHECK("k_pack_rows(z)");
   StepOut o;
   o.do_step = 0;
@@ -643,7 +660,7 @@ extern "C" int32_t aid_sample(const AidScoreDims* dims, const void* packed, void
   AID_TRY(run_obs_encoder(s, w, observation, st));
 
   const int kbl = ceil_div(s.L, TILE_K);
-  k_pack_rows<<<ew_grid((size_t)w.RT * kbl * 1024), 256, 0, st>>>(z_init, batch, s.L, s.L, w.zp, w.RT, kbl, MAP_PLAIN, 0);
+  k_pack_rows<<<ew_grid((size_t)w.RT * kbl * 1024), 256, 0, st>>>(z_init, batch, s.L, s.L, w.zp, w.RT, kbl, MAP_PLAIN, 0, 1);
   AID_LAUNCH_CHECK("k_pack_rows(z)");
   const size_t zl = (size_t)batch * s.L;
   if (traj_out) AID_CHECK(cudaMemcpyAsync(traj_out, z_init, zl * 4, cudaMemcpyDeviceToDevice, st));
@@ -717,7 +734,7 @@ extern "C" int32_t aid_linear(const float* x, const float* wt, const float* bias
   __nv_bfloat16* yp = a.take<__nv_bfloat16>(packed_tiles_bytes(M, p.n_tiles * TILE_N));
   AID_CHECK(cudaMemsetAsync(err, 0, sizeof(int), st));
   const int rt = ceil_div(M, TILE_M);
-  k_pack_rows<<<ew_grid((size_t)rt * p.kb * 1024), 256, 0, st>>>(x, M, K, K, xp, rt, p.kb, MAP_PLAIN, 0);
+  k_pack_rows<<<ew_grid((size_t)rt * p.kb * 1024), 256, 0, st>>>(x, M, K, K, xp, rt, p.kb, MAP_PLAIN, 0, 1);
   AID_LAUNCH_CHECK("k_pack_rows(x)");
   AID_TRY(pack_linear(p, wt, bias, MAP_PLAIN, 0, st));
   EpiArgs e = epi_zero();

@@ -5,26 +5,29 @@
 
 namespace aid {
 
-// One thread per 16-byte chunk (8 bf16) of the packed output.
-// chunk id -> (tile, r, chunk_in_row); tile -> (rt, kb).
+// One thread per 16-byte chunk (8 bf16) of the packed output; consecutive threads take
+// consecutive rows of the same K chunk, i.e. consecutive 16-byte slots of the packed tile.
+// chunk id -> (tile, chunk_in_row, r); tile -> (rt, kb), rt counting 128-row tiles.
 __device__ __forceinline__ void chunk_coords(size_t idx, int kb_total, int& rt, int& kb, int& r,
                                              int& ch) {
-  ch = (int)(idx & 7);
-  r = (int)((idx >> 3) & 127);
+  r = (int)(idx & 127);
+  ch = (int)((idx >> 7) & 7);
   size_t tile = idx >> 10;
   kb = (int)(tile % kb_total);
   rt = (int)(tile / kb_total);
 }
 
+// nw: packed tiles are nw*128 rows tall (weights of N=256 MMAs: nw = 2); rt counts 128-row tiles.
 __device__ __forceinline__ void store_chunk(__nv_bfloat16* dst, int rt, int kb, int kb_total, int r,
-                                            int ch, const float (&v)[8]) {
+                                            int ch, const float (&v)[8], int nw = 1) {
   uint4 o;
   o.x = pack_bf16x2(v[0], v[1]);
   o.y = pack_bf16x2(v[2], v[3]);
   o.z = pack_bf16x2(v[4], v[5]);
   o.w = pack_bf16x2(v[6], v[7]);
-  __nv_bfloat16* tile = dst + ((size_t)rt * kb_total + kb) * TILE_ELEMS;
-  *reinterpret_cast<uint4*>(tile + r * TILE_K + ((ch ^ (r & 7)) << 3)) = o;
+  const int R = nw * TILE_M;
+  __nv_bfloat16* tile = dst + ((size_t)(rt / nw) * kb_total + kb) * ((size_t)nw * TILE_ELEMS);
+  *reinterpret_cast<uint4*>(tile + ch * (R * 8) + ((rt % nw) * TILE_M + r) * 8) = o;
 }
 
 // fp32 row-major [rows, cols] (leading dim ld) -> packed bf16 [row_tiles][kb]; zero padding.
@@ -43,7 +46,7 @@ __device__ __forceinline__ int map_row(int i, int mode, int H) {
 
 __global__ void k_pack_rows(const float* __restrict__ src, int rows, int cols, int ld,
                             __nv_bfloat16* __restrict__ dst, int row_tiles, int kb_total, int mode,
-                            int H) {
+                            int H, int nw) {
   size_t total = (size_t)row_tiles * kb_total * 1024;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -64,7 +67,7 @@ __global__ void k_pack_rows(const float* __restrict__ src, int rows, int cols, i
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       v[i] = (srow >= 0 && c0 + i < cols) ? __ldg(src + (size_t)srow * ld + c0 + i) : 0.f;
-    store_chunk(dst, rt, kb, kb_total, r, ch, v);
+    store_chunk(dst, rt, kb, kb_total, r, ch, v, nw);
   }
 }
 
@@ -88,7 +91,8 @@ __global__ void k_pack_bias(const float* __restrict__ src, int n, float* __restr
 // (models/score_networks.py:189-194,224-227; W_v = in_proj_weight[2H:3H]).
 // Computes the fp32 product and writes packed bf16 tiles directly.
 __global__ void k_pack_folded_attn(const float* __restrict__ in_proj_w, const float* __restrict__ wo,
-                                   int H, __nv_bfloat16* __restrict__ dst, int n_tiles, int kb_total) {
+                                   int H, __nv_bfloat16* __restrict__ dst, int n_tiles, int kb_total,
+                                   int nw) {
   size_t total = (size_t)n_tiles * kb_total * 1024;
   const float* wv = in_proj_w + (size_t)2 * H * H;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -107,7 +111,7 @@ __global__ void k_pack_folded_attn(const float* __restrict__ in_proj_w, const fl
           if (k0 + i < H) acc[i] = fmaf(a, __ldg(row + i), acc[i]);
       }
     }
-    store_chunk(dst, nt, kb, kb_total, r, ch, acc);
+    store_chunk(dst, nt, kb, kb_total, r, ch, acc, nw);
   }
 }
 __global__ void k_folded_attn_bias(const float* __restrict__ in_proj_b, const float* __restrict__ wo,
@@ -200,20 +204,27 @@ struct CondArgs {
   float4* out_tiled;          // c tiled (may be null)
 };
 __global__ void k_cond(const CondArgs a) {
-  // one thread per (row, float4 column); consecutive threads = consecutive rows (coalesced tiled IO)
+  // one thread per (row, 8 columns); consecutive threads = consecutive rows, so the tiled fp32
+  // reads/writes and the 16-byte packed stores are all coalesced
   const int kb_total = (a.H + TILE_K - 1) / TILE_K;
-  size_t total = (size_t)a.row_tiles * a.ld4 * TILE_M;
+  const int nch = a.ld4 / 2;
+  size_t total = (size_t)a.row_tiles * nch * TILE_M;
   const float ts = a.t_cont ? __ldg(a.time_scale) : 0.f;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
-    int r = (int)(idx & 127);
-    int c4 = (int)((idx >> 7) % a.ld4);
-    int rt = (int)((idx >> 7) / a.ld4);
-    int trow = (a.fixed_row >= 0) ? a.fixed_row : rt * TILE_M + r;
-    size_t toff = ((size_t)(trow >> 7) * a.ld4 + c4) * TILE_M + (trow & 127);
-    float4 v = a.t_sin[toff];
-    if (a.t_cont) {
-      float f = a.cont_flag ? __ldg(a.cont_flag + trow) : 1.f;
+    const int r = (int)(idx & 127);
+    const int chn = (int)((idx >> 7) % nch);
+    const int rt = (int)((idx >> 7) / nch);
+    const int trow = (a.fixed_row >= 0) ? a.fixed_row : rt * TILE_M + r;
+    float f = 0.f;
+    if (a.t_cont) f = a.cont_flag ? __ldg(a.cont_flag + trow) : 1.f;
+    float o8[8];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int c4 = chn * 2 + hh;
+      const size_t toff = ((size_t)(trow >> 7) * a.ld4 + c4) * TILE_M + (trow & 127);
+      const size_t boff = ((size_t)rt * a.ld4 + c4) * TILE_M + r;
+      float4 v = a.t_sin[toff];
       if (f != 0.f) {
         float4 c = a.t_cont[toff];
         v.x = __fadd_rn(v.x, __fmul_rn(ts, c.x));
@@ -221,20 +232,17 @@ __global__ void k_cond(const CondArgs a) {
         v.z = __fadd_rn(v.z, __fmul_rn(ts, c.z));
         v.w = __fadd_rn(v.w, __fmul_rn(ts, c.w));
       }
+      if (a.obs_emb) {
+        float4 o = a.obs_emb[boff];
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      if (a.out_tiled) a.out_tiled[boff] = v;
+      o8[hh * 4 + 0] = act_silu(v.x); o8[hh * 4 + 1] = act_silu(v.y);
+      o8[hh * 4 + 2] = act_silu(v.z); o8[hh * 4 + 3] = act_silu(v.w);
     }
-    if (a.obs_emb) {
-      float4 o = a.obs_emb[idx];
-      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-    }
-    if (a.out_tiled) a.out_tiled[idx] = v;
     if (a.out_packed) {
-      int c = c4 * 4;
-      __nv_bfloat16* tile = a.out_packed + ((size_t)rt * kb_total + (c >> 6)) * TILE_ELEMS;
-      int cc = c & 63;
-      uint2 o;
-      o.x = pack_bf16x2(act_silu(v.x), act_silu(v.y));
-      o.y = pack_bf16x2(act_silu(v.z), act_silu(v.w));
-      *reinterpret_cast<uint2*>(tile + r * TILE_K + ((((cc >> 3) ^ (r & 7)) << 3) | (cc & 7))) = o;
+      const int c = chn * 8;
+      if (c < a.H) store_chunk(a.out_packed, rt, c >> 6, kb_total, r, (c >> 3) & 7, o8);
     }
   }
 }

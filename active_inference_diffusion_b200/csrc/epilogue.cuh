@@ -1,24 +1,33 @@
 // Fused epilogues of the tcgen05 GEMM (included by gemm.cuh inside namespace aid).
 //
-// One 128x128 fp32 accumulator tile per call, one thread per row (TMEM lane).  Two phases so
-// that global-memory latency hides behind the MMAs of the same tile:
-//   epi_prefetch : runs BEFORE the accumulator is ready.  Stages the tile's 128 bias values in
-//                  shared memory (one coalesced load per group, then broadcast LDS) and starts the
-//                  loads that do not depend on the accumulator (residual / h rows, LN partials).
-//   epi_finish   : TMEM -> registers (next chunk's load in flight while this chunk is processed),
-//                  math, stores.
+// One 128x128 fp32 accumulator tile per call, one thread per row (TMEM lane).  Every operand an
+// epilogue needs from global memory (bias, residual rows, LayerNorm input rows and statistics) is
+// software-pipelined ACROSS tiles: the registers that held tile i's operands are refilled with
+// tile i+1's as soon as they are consumed, so the loads fly during the rest of tile i's epilogue
+// and tile i+1's MMAs, and nothing waits on HBM/L2 latency when the next accumulator is ready.
+//   epi_first      : loads the operands of a group's first tile.
+//   epi_stage_bias : puts the tile's 128 bias values in shared memory (broadcast reads).
+//   epi_finish     : TMEM -> registers (next chunk's tcgen05.ld in flight while this chunk is
+//                    processed), math, stores, refill for the group's next tile (rt2, nt2).
+// The 32-column chunk loops are deliberately NOT fully unrolled: the fully unrolled kernels were
+// 150-250 KB of SASS and stalled on instruction fetch (ncu: stall_no_instruction on top).
 // rt/nt: row tile / n-tile indices; r: row inside the tile.
 
 template <int EPI>
-struct EpiPre {};
-template <>
-struct EpiPre<EPI_F32> {
-  float4 res[2][8];  // residual chunks c and c+1 (double buffer)
+struct EpiState {
+  float bias;        // bias[nt*128 + r] of the tile about to be processed
 };
 template <>
-struct EpiPre<EPI_MODLN> {
-  float4 h[16];      // the 64 hidden columns this tile normalises
+struct EpiState<EPI_F32> {
+  float bias;
+  float4 res[2][8];  // residual chunks 0 and 1 of the tile about to be processed
+};
+template <>
+struct EpiState<EPI_MODLN> {
+  float bias;
+  float4 h[16];      // the 64 hidden columns the tile normalises
   float mean, rstd;
+  int rt;            // row tile the statistics belong to
 };
 
 __device__ __forceinline__ void bias32_from_smem(const float* sb, int c0, float (&b)[32]) {
@@ -34,144 +43,191 @@ __device__ __forceinline__ void group_bar(int bar_id) {
   asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 }
 
-template <int EPI>
-__device__ __forceinline__ void epi_prefetch(const EpiArgs& e, int rt, int nt, int r, float* sb,
-                                             int bar_id, EpiPre<EPI>& pre) {
-  if constexpr (EPI != EPI_SCORE) {
-    const float bv = e.bias ? __ldg(e.bias + nt * TILE_N + r) : 0.f;
-    group_bar(bar_id);  // every reader of the previous tile's stage is done
-    sb[r] = bv;
+template <int ACT>
+__device__ __forceinline__ void act_apply32_ct(float (&y)[32]) {
+  if constexpr (ACT == ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = act_silu(y[j]);
+  } else if constexpr (ACT == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+  } else if constexpr (ACT == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = act_gelu(y[j]);
   }
+}
+
+__device__ __forceinline__ void modln_stats(const EpiArgs& e, int rt, int r, float& mean, float& rstd) {
+  float sn = 0.f, m = 0.f, m2 = 0.f;
+  for (int p = 0; p < e.stats_nt; ++p) {
+    float2 s = e.stats_in[((size_t)rt * e.stats_nt + p) * TILE_M + r];
+    stats_merge(sn, m, m2, (float)min(TILE_N, e.h_dim - p * TILE_N), s.x, s.y);
+  }
+  mean = m;
+  rstd = rsqrtf(m2 / (float)e.h_dim + 1e-5f);
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_first(const EpiArgs& e, int rt, int nt, int r, EpiState<EPI>& st) {
+  st.bias = 0.f;
+  if constexpr (EPI != EPI_SCORE) st.bias = e.bias ? __ldg(e.bias + nt * TILE_N + r) : 0.f;
   if constexpr (EPI == EPI_F32) {
     if (e.resid_tiled) {
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          pre.res[c][q] =
+          st.res[c][q] =
               e.resid_tiled[((size_t)rt * e.ld4 + ((nt * TILE_N + c * 32) >> 2) + q) * TILE_M + r];
     }
   } else if constexpr (EPI == EPI_MODLN) {
 #pragma unroll
     for (int q = 0; q < 16; ++q)
-      pre.h[q] = e.h_tiled[((size_t)rt * e.h_ld4 + nt * 16 + q) * TILE_M + r];
-    float sn = 0.f, mean = 0.f, m2 = 0.f;
-    for (int p = 0; p < e.stats_nt; ++p) {
-      float2 s = e.stats_in[((size_t)rt * e.stats_nt + p) * TILE_M + r];
-      stats_merge(sn, mean, m2, (float)min(TILE_N, e.h_dim - p * TILE_N), s.x, s.y);
-    }
-    pre.mean = mean;
-    pre.rstd = rsqrtf(m2 / (float)e.h_dim + 1e-5f);
+      st.h[q] = e.h_tiled[((size_t)rt * e.h_ld4 + nt * 16 + q) * TILE_M + r];
+    modln_stats(e, rt, r, st.mean, st.rstd);
+    st.rt = rt;
   }
-  if constexpr (EPI != EPI_SCORE) group_bar(bar_id);  // stage visible to the whole group
 }
 
+// Stage this tile's bias in shared memory and start the load of the next tile's.
 template <int EPI>
+__device__ __forceinline__ void epi_stage_bias(const EpiArgs& e, float* sb, int bar_id, int r,
+                                               EpiState<EPI>& st, bool has_next, int nt2) {
+  if constexpr (EPI != EPI_SCORE) {
+    group_bar(bar_id);  // every reader of the previous tile's stage is done
+    sb[r] = st.bias;
+    st.bias = (has_next && e.bias) ? __ldg(e.bias + nt2 * TILE_N + r) : 0.f;
+    group_bar(bar_id);  // stage visible to the whole group
+  }
+}
+
+template <int EPI, int ACT>
 __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile, int rt, int nt,
-                                           int n_tiles, int r, const float* sb, EpiPre<EPI>& pre) {
+                                           int n_tiles, int r, const float* sb, EpiState<EPI>& st,
+                                           bool has_next, int rt2, int nt2) {
   const int row = rt * TILE_M + r;
 
   if constexpr (EPI == EPI_PACK) {
-    uint32_t raw[2][32];
-    tmem_ld32(tmem_tile, raw[0]);
+    uint32_t raw[32];
+    tmem_ld32(tmem_tile, raw);
+#pragma unroll 1
+    for (int cc = 0; cc < 4; cc += 2) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int n0 = nt * TILE_N + c * 32;
-      float y[32];
-      bias32_from_smem(sb, c * 32, y);
-      tmem_ld_wait();
-      if (c + 1 < 4) tmem_ld32(tmem_tile + (c + 1) * 32, raw[(c + 1) & 1]);
+      for (int hb = 0; hb < 2; ++hb) {
+        const int c = cc + hb;
+        const int n0 = nt * TILE_N + c * 32;
+        float y[32];
+        bias32_from_smem(sb, c * 32, y);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[c & 1][j]);
-      act_apply32(y, e.act);
-      if (n0 + 32 > e.n_valid) {
+        for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
+        if (c + 1 < 4) tmem_ld32(tmem_tile + (c + 1) * 32, raw);   // in flight during this chunk's math
+        act_apply32_ct<ACT>(y);
+        if (n0 + 32 > e.n_valid) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
-      }
-      const int kb_out = n0 >> 6;
-      if (kb_out < e.out_kb) {
-        __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
-        store_packed32(tile, r, n0 & 63, y);
+          for (int j = 0; j < 32; ++j) y[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
+        }
+        const int kb_out = n0 >> 6;
+        if (kb_out < e.out_kb) {
+          __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
+          store_packed32(tile, r, n0 & 63, y);
+        }
       }
     }
   } else if constexpr (EPI == EPI_F32) {
     float sn = 0.f, smean = 0.f, sm2 = 0.f;
     uint32_t raw[32];
+    tmem_ld32(tmem_tile, raw);
+#pragma unroll 1
+    for (int cc = 0; cc < 4; cc += 2) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int n0 = nt * TILE_N + c * 32;
-      float y[32];
-      tmem_ld32(tmem_tile + c * 32, raw);
-      bias32_from_smem(sb, c * 32, y);
-      tmem_ld_wait();
+      for (int hb = 0; hb < 2; ++hb) {
+        const int c = cc + hb;
+        const int n0 = nt * TILE_N + c * 32;
+        float y[32];
+        bias32_from_smem(sb, c * 32, y);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
-      if (e.resid_tiled) {
+        for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
+        if (c + 1 < 4) tmem_ld32(tmem_tile + (c + 1) * 32, raw);   // in flight during this chunk's math
+        if (e.resid_tiled) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 hv = pre.res[c & 1][q];
-          y[q * 4 + 0] += hv.x; y[q * 4 + 1] += hv.y; y[q * 4 + 2] += hv.z; y[q * 4 + 3] += hv.w;
+          for (int q = 0; q < 8; ++q) {
+            float4 hv = st.res[hb][q];
+            y[q * 4 + 0] += hv.x; y[q * 4 + 1] += hv.y; y[q * 4 + 2] += hv.z; y[q * 4 + 3] += hv.w;
+          }
+          // refill this buffer: chunk c+2 of this tile, or chunk c-2 of the group's next tile
+          if (c < 2) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              st.res[hb][q] = e.resid_tiled[((size_t)rt * e.ld4 + ((n0 + 64) >> 2) + q) * TILE_M + r];
+          } else if (has_next) {
+            const int m0 = nt2 * TILE_N + (c - 2) * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              st.res[hb][q] = e.resid_tiled[((size_t)rt2 * e.ld4 + (m0 >> 2) + q) * TILE_M + r];
+          }
         }
-        if (c + 2 < 4) {  // refill this buffer with chunk c+2 while chunk c+1 is processed
+        act_apply32_ct<ACT>(y);
+        if (e.out_tiled) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            pre.res[c & 1][q] =
-                e.resid_tiled[((size_t)rt * e.ld4 + ((n0 + 64) >> 2) + q) * TILE_M + r];
+            e.out_tiled[((size_t)rt * e.ld4 + (n0 >> 2) + q) * TILE_M + r] =
+                make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
         }
-      }
-      act_apply32(y, e.act);
-      if (e.out_tiled) {
+        if (e.out_packed && (n0 >> 6) < e.out_kb) {
+          float yp[32];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          e.out_tiled[((size_t)rt * e.ld4 + (n0 >> 2) + q) * TILE_M + r] =
-              make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
-      }
-      if (e.out_packed && (n0 >> 6) < e.out_kb) {
-        float yp[32];
+          for (int j = 0; j < 32; ++j) yp[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
+          __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + (n0 >> 6)) * TILE_ELEMS;
+          store_packed32(tile, r, n0 & 63, yp);
+        }
+        if (e.out_rm && row < e.rows_valid) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) yp[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
-        __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + (n0 >> 6)) * TILE_ELEMS;
-        store_packed32(tile, r, n0 & 63, yp);
-      }
-      if (e.out_rm && row < e.rows_valid) {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < e.n_valid) e.out_rm[(size_t)row * e.ld_rm + n0 + j] = y[j];
+        }
+        if (e.stats_out) {
+          int nv = min(32, max(0, e.n_valid - n0));
+          if (nv > 0) {
+            float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + j < e.n_valid) e.out_rm[(size_t)row * e.ld_rm + n0 + j] = y[j];
-      }
-      if (e.stats_out) {
-        int nv = min(32, max(0, e.n_valid - n0));
-        if (nv > 0) {
-          float s = 0.f;
+            for (int j = 0; j < 32; ++j) s += (j < nv) ? y[j] : 0.f;
+            float m = s / (float)nv;
+            float q2 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s += (j < nv) ? y[j] : 0.f;
-          float m = s / (float)nv;
-          float q2 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float d = (j < nv) ? (y[j] - m) : 0.f;
-            q2 += d * d;
+            for (int j = 0; j < 32; ++j) {
+              float d = (j < nv) ? (y[j] - m) : 0.f;
+              q2 += d * d;
+            }
+            stats_merge(sn, smean, sm2, (float)nv, m, q2);
           }
-          stats_merge(sn, smean, sm2, (float)nv, m, q2);
         }
       }
     }
     if (e.stats_out) e.stats_out[((size_t)rt * n_tiles + nt) * TILE_M + r] = make_float2(smean, sm2);
   } else if constexpr (EPI == EPI_MODLN) {
-    const float mean = pre.mean, rstd = pre.rstd;
+    const float mean = st.mean, rstd = st.rstd;
     __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + nt) * TILE_ELEMS;
+    uint32_t rs[16], rh[16];
+    tmem_ld16(tmem_tile, rs);                     // scale cols
+    tmem_ld16(tmem_tile + 64, rh);                // shift cols
 #pragma unroll
     for (int c = 0; c < 4; ++c) {                 // 16 hidden columns per iteration
-      uint32_t rs[16], rh[16];
-      tmem_ld16(tmem_tile + c * 16, rs);          // scale cols
-      tmem_ld16(tmem_tile + 64 + c * 16, rh);     // shift cols
       const float4* bsp = reinterpret_cast<const float4*>(sb + c * 16);        // scale biases
       const float4* bhp = reinterpret_cast<const float4*>(sb + 64 + c * 16);   // shift biases
       const int hc0 = nt * 64 + c * 16;           // hidden column of y[0]
-      float y[16];
+      float y[16], sc[16], sh[16];
       tmem_ld_wait();
 #pragma unroll
+      for (int j = 0; j < 16; ++j) { sc[j] = __uint_as_float(rs[j]); sh[j] = __uint_as_float(rh[j]); }
+      if (c + 1 < 4) {                            // next chunk's accumulators in flight during the math
+        tmem_ld16(tmem_tile + (c + 1) * 16, rs);
+        tmem_ld16(tmem_tile + 64 + (c + 1) * 16, rh);
+      }
+#pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 hv = pre.h[c * 4 + q];
+        const float4 hv = st.h[c * 4 + q];
         const float4 b1 = bsp[q], b2 = bhp[q];
         const float hx[4] = {hv.x, hv.y, hv.z, hv.w};
         const float bs[4] = {b1.x, b1.y, b1.z, b1.w};
@@ -179,11 +235,16 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int j = q * 4 + i;
-          const float scale = __uint_as_float(rs[j]) + bs[i];
-          const float shift = __uint_as_float(rh[j]) + bh[i];
+          const float scale = sc[j] + bs[i];
+          const float shift = sh[j] + bh[i];
           const float xn = (hx[i] - mean) * rstd;
           y[j] = (hc0 + j < e.h_dim) ? fmaf(xn, 1.0f + scale, shift) : 0.f;
         }
+      }
+      if (has_next) {                             // refill the consumed registers for the next tile
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          st.h[c * 4 + q] = e.h_tiled[((size_t)rt2 * e.h_ld4 + nt2 * 16 + c * 4 + q) * TILE_M + r];
       }
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -193,8 +254,12 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
         v.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
         v.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
         const int chunk = c * 2 + q;
-        *reinterpret_cast<uint4*>(tile + r * TILE_K + ((chunk ^ (r & 7)) << 3)) = v;
+        *reinterpret_cast<uint4*>(tile + chunk * (TILE_M * 8) + r * 8) = v;
       }
+    }
+    if (has_next && rt2 != st.rt) {               // LayerNorm statistics change with the row tile only
+      modln_stats(e, rt2, r, st.mean, st.rstd);
+      st.rt = rt2;
     }
   } else {  // EPI_SCORE
     uint32_t raw[32];
@@ -205,9 +270,21 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
       const int n0 = nt * TILE_N + c * 32;
       if (n0 >= e.n_valid && !e.out_packed) break;
       tmem_ld32(tmem_tile + c * 32, raw);
+      const bool live = row < e.rows_valid;
+      // the step's operands do not depend on the accumulator: load them under the TMEM latency
+      float4 zv[8], ev[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int col = n0 + q * 4;
+        zv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ev[q] = zv[q];
+        if (e.do_step && live && (col + 3 < e.n_valid)) {
+          zv[q] = *reinterpret_cast<const float4*>(e.z_in + (size_t)row * e.n_valid + col);
+          if (e.eps) ev[q] = *reinterpret_cast<const float4*>(e.eps + (size_t)row * e.n_valid + col);
+        }
+      }
       tmem_ld_wait();
       float y[32];
-      const bool live = row < e.rows_valid;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float s = fminf(fmaxf(__uint_as_float(raw[j]), -10.f), 10.f);
@@ -219,13 +296,8 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int col = n0 + q * 4;
-          float4 zv = make_float4(0.f, 0.f, 0.f, 0.f), ev = zv;
           const bool ok = live && (col + 3 < e.n_valid);
-          if (ok) {
-            zv = *reinterpret_cast<const float4*>(e.z_in + (size_t)row * e.n_valid + col);
-            if (e.eps) ev = *reinterpret_cast<const float4*>(e.eps + (size_t)row * e.n_valid + col);
-          }
-          float zz[4] = {zv.x, zv.y, zv.z, zv.w}, ee[4] = {ev.x, ev.y, ev.z, ev.w};
+          float zz[4] = {zv[q].x, zv[q].y, zv[q].z, zv[q].w}, ee[4] = {ev[q].x, ev[q].y, ev[q].z, ev[q].w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             // (z + s1*score) * ra ; c1*pred + c2*z ; + sigma*eps   (rounding order of the reference)

@@ -3,9 +3,14 @@
 //   D[128 x 128] (TMEM, fp32) = A[128 x K] (bf16, K-major, SW128 tiles) * B[128 x K]^T
 //
 // Data layout in HBM (all produced by this library, never by the caller):
-//   * "packed" bf16 operand  : [row_tile][k_block] tiles of 128 rows x 64 cols, each tile 16 KiB
-//     contiguous and already in the 128-byte-swizzled shared-memory image, so one
-//     cp.async.bulk (TMA engine) moves a tile and the UMMA descriptor reads it directly.
+//   * "packed" bf16 operand  : [row_tile][k_block] tiles of R rows x 64 cols (R = 128 for
+//     activations, 128 or 256 for weights), each tile R*128 bytes contiguous and already the
+//     shared-memory image of the K-major NO-swizzle UMMA layout: [16-byte K chunk (8)][row (R)][8 bf16].
+//     One cp.async.bulk (TMA engine) moves a tile and the UMMA descriptor reads it directly.  With
+//     one thread per row, a warp writing one K chunk stores 512 contiguous bytes: epilogues and pack
+//     kernels write packed operands with fully coalesced 16-byte stores (the 128-byte-swizzled
+//     image needs 32 different 128-byte lines per warp store and was L1TEX-wavefront bound), and
+//     the tensor pipe reads it at the same rate (scripts/micro/mma_rate.cu: 128 cyc per N=256 MMA).
 //   * "tiled" fp32 activation: [row_tile][col/4][128 rows] float4, so that the epilogue's
 //     one-thread-per-row accesses are fully coalesced.
 //   * LayerNorm partials     : [row_tile][n_tile][128 rows] float2 (mean, M2) per 128 columns.
@@ -85,8 +90,9 @@ struct EpiArgs {
   float* z_out;              // row-major fp32 (score or new z)
 };
 
-__device__ __forceinline__ int packed_off(int r, int c) {  // element offset inside a 128x64 tile
-  return r * TILE_K + ((((c >> 3) ^ (r & 7)) << 3) | (c & 7));
+// element offset of (row r, col c) inside an R-row x 64-col packed tile
+__device__ __forceinline__ int packed_off(int r, int c, int R = TILE_M) {
+  return (c >> 3) * (R * 8) + r * 8 + (c & 7);
 }
 
 __device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
@@ -144,7 +150,7 @@ __device__ __forceinline__ void store_packed32(__nv_bfloat16* tile_base, int r, 
     v.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
     v.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
     int chunk = (c0_in_tile >> 3) + q;
-    *reinterpret_cast<uint4*>(tile_base + r * TILE_K + ((chunk ^ (r & 7)) << 3)) = v;
+    *reinterpret_cast<uint4*>(tile_base + chunk * (TILE_M * 8) + r * 8) = v;
   }
 }
 
@@ -184,7 +190,8 @@ static_assert(sizeof(GemmCtrl) == SMEM_CTRL, "control block must be exactly SMEM
 // G   : MMA units accumulated concurrently (they share each streamed A k-block).
 // RES : A row tile resident in shared memory (kb <= MAX_RES_KB) vs streamed through the ring.
 // A "unit" is TU = NW*G consecutive n-tiles of one row tile; TMEM holds 4/TU units in flight.
-template <int EPI, int NW, int G, bool RES>
+// ACT : activation of EPI_PACK / EPI_F32 resolved at compile time (the others take ACT_NONE).
+template <int EPI, int NW, int G, bool RES, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
   constexpr int TU = NW * G;
@@ -264,13 +271,9 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
             if (ga.debug & 2) {
               mbar_arrive(fb);
             } else {
-              mbar_arrive_expect_tx(fb, SLOT_BYTES);
-#pragma unroll
-              for (int j = 0; j < NW; ++j) {
-                const int nt = (ng * G + g) * NW + j;
-                bulk_g2s(ring_smem + stage * SLOT_BYTES + j * TILE_BYTES,
-                         ga.B + ((size_t)nt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
-              }
+              mbar_arrive_expect_tx(fb, SLOT_BYTES);   // weight tiles are packed NW*128 rows tall
+              bulk_g2s(ring_smem + stage * SLOT_BYTES,
+                       ga.B + ((size_t)(ng * G + g) * ga.kb + kb) * SLOT_BYTES, SLOT_BYTES, fb);
             }
             if (++stage == ring_stages) { stage = 0; phase ^= 1; }
           }
@@ -319,7 +322,8 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
             const uint32_t d = tmem_base + (uint32_t)(((q + g * NW) & 3) * TILE_N);
 #pragma unroll
             for (int k = 0; k < TILE_K / 16; ++k) {
-              umma_bf16(d, umma_desc_sw128(a_tile + k * 32), umma_desc_sw128(b_tile + k * 32), idesc,
+              umma_bf16(d, umma_desc_kmajor(a_tile + k * (2 * TILE_M * 16), TILE_M * 16),
+                        umma_desc_kmajor(b_tile + k * (2 * NW * TILE_M * 16), NW * TILE_M * 16), idesc,
                         (kb | k) ? 1u : 0u);
             }
             umma_commit(smem_u32(&ctrl->ring_empty[stage]));
@@ -336,28 +340,40 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
     }
   } else if (warp >= 4) {
     // ===================== epilogue (two groups of 4 warps) =====================
-    const int eg = (warp - 4) >> 2;     // group 0/1 handles tile sequence numbers of that parity
+    // Group eg owns the tiles with sequence number q = eg, eg+2, ... of this CTA (q counts 128-col
+    // tiles in MMA order; accumulator slot q & 3, use count q >> 2).
+    const int eg = (warp - 4) >> 2;
     const int lq = warp & 3;            // TMEM lane quadrant this warp may access
     const int r = lq * 32 + lane;
-    int q = 0;
-    for (int u = u_begin; u < u_end; ++u) {
+    const int n_local = (u_end - u_begin) * TU;
+    float* sb = ctrl->bias_stage[eg];
+    auto coords = [&](int q, int& rt, int& nt) {
+      const int u = u_begin + q / TU;
       const int ue = ga.reverse ? num_units - 1 - u : u;
-      const int rt = ue / groups, ng = ue % groups;
-#pragma unroll
-      for (int t = 0; t < TU; ++t, ++q) {
-        if ((q & 1) != eg) continue;
-        const int buf = q & 3, use = q >> 2;
-        EpiPre<EPI> pre;
-        float* sb = ctrl->bias_stage[eg];
-        if (!(ga.debug & 1)) epi_prefetch<EPI>(ea, rt, ng * TU + t, r, sb, 1 + eg, pre);
-        mbar_wait(smem_u32(&ctrl->acc_full[buf]), use & 1, ga.err, 8);
-        tc_fence_after();
-        const uint32_t tm = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
-        if (!(ga.debug & 1)) epi_finish<EPI>(ea, tm, rt, ng * TU + t, ga.n_tiles, r, sb, pre);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&ctrl->acc_empty[buf]));
-      }
+      rt = ue / groups;
+      nt = (ue % groups) * TU + q % TU;
+    };
+    EpiState<EPI> st;
+    int rt = 0, nt = 0;
+    if (eg < n_local && !(ga.debug & 1)) {
+      coords(eg, rt, nt);
+      epi_first<EPI>(ea, rt, nt, r, st);
+    }
+#pragma unroll 1
+    for (int q = eg; q < n_local; q += 2) {
+      coords(q, rt, nt);
+      const bool has_next = q + 2 < n_local;
+      int rt2 = rt, nt2 = nt;
+      if (has_next) coords(q + 2, rt2, nt2);
+      const int buf = q & 3, use = q >> 2;
+      if (!(ga.debug & 1)) epi_stage_bias<EPI>(ea, sb, 1 + eg, r, st, has_next, nt2);
+      mbar_wait(smem_u32(&ctrl->acc_full[buf]), use & 1, ga.err, 8);
+      tc_fence_after();
+      const uint32_t tm = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
+      if (!(ga.debug & 1)) epi_finish<EPI, ACT>(ea, tm, rt, nt, ga.n_tiles, r, sb, st, has_next, rt2, nt2);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ctrl->acc_empty[buf]));
     }
   }
 

@@ -66,6 +66,28 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src
       ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
+// shared -> global bulk store (TMA engine), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA) of this CTA
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -149,6 +171,15 @@ __device__ __forceinline__ void tmem_ld_wait() {
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) |
          (1ull << 46) | (2ull << 61);
+}
+// Shared-memory matrix descriptor, K-major operand, NO swizzle ("interleaved" canonical layout,
+// CUTLASS: ((8,n),2):((1,SBO),LBO) in 16-byte units): a core matrix is 8 rows x 16 bytes stored
+// contiguously (128 B); SBO = byte distance between consecutive 8-row groups, LBO = byte distance
+// between the two 16-byte K chunks of one K=16 MMA.  Our operand tiles store, for each 16-byte
+// K chunk, all R rows contiguously: SBO = 128, LBO = R*16.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) |
+         (static_cast<uint64_t>(lbo_bytes >> 4) << 16) | (8ull << 32) | (1ull << 46);
 }
 // Instruction descriptor: D=f32 (bits 4-5 =1), A=B=bf16 (bits 7-9, 10-12 =1), both K-major,
 // N>>3 at bit 17, M>>4 at bit 24.
