@@ -11,6 +11,7 @@
 #include "../../include/aid_b200.h"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 
 using namespace aid;
 
@@ -95,12 +96,22 @@ struct PLin {
   int nw = 1;              // packed tile height in n-tiles: 2 -> 256-row tiles for N=256 MMAs
 };
 
+// CTA-pair kernels (gemm2.cuh, tcgen05 cta_group::2) are opt-in (AID_PAIRS=1): they are correct
+// (the whole GPU suite passes with them) but measured SLOWER than the single-CTA kernels on B200
+// for this network (DESIGN.md "what was tried"): the single-CTA MMA stream already runs at the
+// power-limited tensor rate with or without weight loads, so halving weight traffic buys nothing,
+// while the leader's single issue thread pays three mbarrier waits per 512-cycle stage.
+static bool use_pairs() {
+  static const bool on = getenv("AID_PAIRS") && atoi(getenv("AID_PAIRS")) != 0;
+  return on;
+}
+
 static void plin_shape(PLin& p, int n, int k, bool modln = false) {
   p.n = n;
   p.k = k;
   p.kb = ceil_div(k, TILE_K);
   p.n_tiles = modln ? ceil_div(n / 2, 64) : ceil_div(n, TILE_N);
-  p.nw = (p.n_tiles % 2 == 0) ? 2 : 1;
+  p.nw = (!use_pairs() && p.n_tiles % 2 == 0) ? 2 : 1;
 }
 static size_t plin_w_bytes(const PLin& p) { return (size_t)p.n_tiles * p.kb * TILE_BYTES; }
 static size_t plin_b_bytes(const PLin& p) { return (size_t)p.n_tiles * TILE_N * sizeof(float); }
@@ -186,8 +197,39 @@ static int launch_gemm_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t 
   return 0;
 }
 
+template <int EPI, bool RES, int ACT>
+static int launch_gemm2_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = gemm2_kernel<EPI, RES, ACT>;
+  if (!configured) {
+    AID_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    configured = true;
+  }
+  const int a_bytes = RES ? ga.kb * TILE_BYTES : 0;
+  const int slot = (RES ? 1 : 2) * TILE_BYTES;
+  int ring = (SMEM_LIMIT - 1024 - SMEM_CTRL - a_bytes) / slot;
+  if (ring > MAX_RING2) ring = MAX_RING2;
+  if (ring < 2) return fail("gemm2: not enough shared memory for the ring");
+  const size_t smem = 1024 + SMEM_CTRL + a_bytes + (size_t)ring * slot;
+  const int units = ((ga.row_tiles + 1) / 2) * (ga.n_tiles / 2);
+  const int max_pairs = num_sms() / 2;
+  const int pairs = units < max_pairs ? units : max_pairs;
+  if (pairs < 1) return 0;
+  const bool prof = g_prof.on && g_prof.epi == EPI && g_prof.kb == ga.kb && g_prof.n_tiles == ga.n_tiles &&
+                    g_prof.used < 200000;
+  if (prof) cudaEventRecord(prof_event(), st);
+  kern<<<2 * pairs, GEMM_THREADS, smem, st>>>(ga, ea, ring);
+  if (prof) cudaEventRecord(prof_event(), st);
+  AID_LAUNCH_CHECK("gemm2_kernel");
+  return 0;
+}
+
 template <int EPI, int ACT>
 static int launch_gemm_shape(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t st, bool res, bool wide) {
+  if (use_pairs() && ga.n_tiles % 2 == 0) {
+    if (res) return launch_gemm2_inst<EPI, true, ACT>(ga, ea, st);
+    return launch_gemm2_inst<EPI, false, ACT>(ga, ea, st);
+  }
   if (res) {
     if (wide) return launch_gemm_inst<EPI, 2, 1, true, ACT>(ga, ea, st);
     return launch_gemm_inst<EPI, 1, 1, true, ACT>(ga, ea, st);
@@ -208,6 +250,7 @@ static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs e
   ga.err = err_flag;
   static const int dbg = getenv("AID_DEBUG") ? atoi(getenv("AID_DEBUG")) : 0;
   ga.debug = dbg;
+  ea.debug = dbg;
   // Consecutive GEMMs of a chain walk the row tiles in opposite directions: the tiles the
   // previous kernel wrote LAST are the ones this kernel reads FIRST, so they are still in the
   // 126 MB L2 instead of coming back from HBM (activations of a 65k-row batch exceed L2).

@@ -122,13 +122,13 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
         if (c + 1 < 4) tmem_ld32(tmem_tile + (c + 1) * 32, raw);   // in flight during this chunk's math
-        act_apply32_ct<ACT>(y);
+        if (!(e.debug & 64)) act_apply32_ct<ACT>(y);
         if (n0 + 32 > e.n_valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) y[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
         }
         const int kb_out = n0 >> 6;
-        if (kb_out < e.out_kb) {
+        if (kb_out < e.out_kb && !(e.debug & 32)) {
           __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
           store_packed32(tile, r, n0 & 63, y);
         }
@@ -150,7 +150,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
         if (c + 1 < 4) tmem_ld32(tmem_tile + (c + 1) * 32, raw);   // in flight during this chunk's math
-        if (e.resid_tiled) {
+        if (e.resid_tiled && !(e.debug & 128)) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float4 hv = st.res[hb][q];
@@ -169,7 +169,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
           }
         }
         act_apply32_ct<ACT>(y);
-        if (e.out_tiled) {
+        if (e.out_tiled && !(e.debug & 32)) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             e.out_tiled[((size_t)rt * e.ld4 + (n0 >> 2) + q) * TILE_M + r] =
@@ -241,11 +241,12 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
           y[j] = (hc0 + j < e.h_dim) ? fmaf(xn, 1.0f + scale, shift) : 0.f;
         }
       }
-      if (has_next) {                             // refill the consumed registers for the next tile
+      if (has_next && !(e.debug & 128)) {         // refill the consumed registers for the next tile
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           st.h[c * 4 + q] = e.h_tiled[((size_t)rt2 * e.h_ld4 + nt2 * 16 + c * 4 + q) * TILE_M + r];
       }
+      if (!(e.debug & 32))
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         uint4 v;

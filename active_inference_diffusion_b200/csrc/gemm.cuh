@@ -59,6 +59,8 @@ struct GemmArgs {
 };
 
 struct EpiArgs {
+  int debug;           // developer knobs (AID_DEBUG): 32 = no epilogue stores, 64 = no activation,
+                       // 128 = no epilogue global loads (residual / LayerNorm rows)
   const float* bias;   // [n_tiles*128] (padded), may be null
   int act;
   int n_valid;         // number of real output columns

@@ -1,0 +1,307 @@
+// CTA-pair (cta_group::2) variant of the persistent tcgen05 GEMM.
+//
+// Why: with one CTA per 128-row tile every SM streams the FULL weight matrix of a layer through
+// its L2->shared-memory port: 64 B/clk/SM at the tensor-pipe rate, 10-15 TB/s over the chip.
+// Measured on B200 (scripts/perf_kernels.py) every hot GEMM of the score network ran at
+// (weight + activation bytes) / ~10.4 TB/s whether or not its epilogue did anything -- the L2
+// fabric, not the tensor pipe, set the time.  Pairing two SMs on one 256-row x 256-col UMMA
+// (tcgen05.mma.cta_group::2) lets each CTA fetch only HALF of every weight tile (its 128 of the
+// 256 weight rows); the pair's tensor cores read both halves.  Weight traffic per SM halves.
+//
+// Layout per CTA (rank c of the pair):
+//   A  : its own 128-row activation tile (row tile 2*rp + c), resident (K <= 512) or streamed.
+//   B  : 128 x 64 half tiles (n-tile 2*ng + c of the 256-column unit) in a ring of stages.
+//   D  : TMEM accumulators of its own 128 rows x 256 columns, two units in flight.
+// Protocol (all mbarriers in each CTA's control block at identical offsets):
+//   ring_full[s]  local   : the CTA's own bulk copies (complete_tx).
+//   peer_full[s]  leader  : rank 1's "forwarder" thread waits on its local a_full/ring_full and
+//                           arrives remotely here, so the leader's single MMA thread knows both
+//                           halves (and rank 1's A k-block) are in shared memory.
+//   ring_empty[s], a_empty[kb], acc_full[slot] : signalled in BOTH CTAs by the leader's
+//                           tcgen05.commit ... multicast::cluster (mask 0b11).
+//   acc_empty[slot] leader : 8 arrivals = 4 epilogue warps of each CTA (rank 1 arrives remotely).
+// Only rank 0 issues MMAs.  Epilogues are the per-CTA ones of epilogue.cuh, unchanged.
+#pragma once
+#include "gemm.cuh"
+
+namespace aid {
+
+constexpr int MAX_RING2 = 12;
+
+struct alignas(8) Gemm2Ctrl {
+  uint64_t ring_full[MAX_RING2];
+  uint64_t ring_empty[MAX_RING2];
+  uint64_t peer_full[MAX_RING2];
+  uint64_t a_full[MAX_RES_KB];
+  uint64_t a_empty[MAX_RES_KB];
+  uint64_t acc_full[4];
+  uint64_t acc_empty[4];
+  uint32_t tmem_base;
+  uint32_t pad_[(1024 - (3 * MAX_RING2 + 2 * MAX_RES_KB + 8) * 8 - 4) / 4];
+  float bias_stage[2][TILE_N];   // per epilogue group; 1024-byte offset
+  uint8_t pad2_[SMEM_CTRL - 1024 - 2 * TILE_N * 4];
+};
+static_assert(sizeof(Gemm2Ctrl) == SMEM_CTRL, "control block must be exactly SMEM_CTRL bytes");
+
+// ---- cluster / cta_group::2 PTX -----------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[tmem, 256 rows over the pair] (+)= A * B^T, issued by the leader CTA only
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (same offset in both CTAs of the pair) once all tcgen05 ops issued so far completed
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+
+// RES : A row tile resident in shared memory (kb <= MAX_RES_KB) vs streamed with the B halves.
+// A "pair unit" = (row-tile pair rp, 256-column group ng); rank c owns row tile 2*rp + c.
+template <int EPI, bool RES, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
+  constexpr int TU = 2;                                       // 128-col tiles per unit
+  constexpr int STAGE_BYTES2 = (RES ? 1 : 2) * TILE_BYTES;    // [A k-block |] B half tile
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;          // same offset in both CTAs
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  Gemm2Ctrl* ctrl = reinterpret_cast<Gemm2Ctrl*>(smem);
+  const uint32_t a_smem = base + SMEM_CTRL;
+  const uint32_t ring_smem = a_smem + (RES ? ga.kb * TILE_BYTES : 0);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int groups = ga.n_tiles / TU;                         // units per row-tile pair
+  const int rps = (ga.row_tiles + 1) >> 1;
+  const int num_units = rps * groups;
+  const int u_begin = (int)((long long)pair * num_units / num_pairs);
+  const int u_end = (int)((long long)(pair + 1) * num_units / num_pairs);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_RING2; ++i) {
+      mbar_init(smem_u32(&ctrl->ring_full[i]), 1);
+      mbar_init(smem_u32(&ctrl->ring_empty[i]), 1);
+      mbar_init(smem_u32(&ctrl->peer_full[i]), 1);
+    }
+    for (int i = 0; i < MAX_RES_KB; ++i) {
+      mbar_init(smem_u32(&ctrl->a_full[i]), 1);
+      mbar_init(smem_u32(&ctrl->a_empty[i]), 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(smem_u32(&ctrl->acc_full[i]), 1);
+      mbar_init(smem_u32(&ctrl->acc_empty[i]), 8);  // 4 epilogue warps of each CTA
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(smem_u32(&ctrl->tmem_base), 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();                                         // barriers of BOTH CTAs are live
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+
+  auto unit_coords = [&](int u, int& rp, int& ng) {
+    const int ue = ga.reverse ? num_units - 1 - u : u;
+    rp = ue / groups;
+    ng = ue % groups;
+  };
+
+  if (warp == 0) {
+    // ===================== producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, a_par = 0;
+      int prev_rp = -1;
+      for (int u = u_begin; u < u_end; ++u) {
+        int rp, ng;
+        unit_coords(u, rp, ng);
+        const int rt = min(2 * rp + (int)rank, ga.row_tiles - 1);   // odd tail: reload a valid tile
+        const int nt = ng * TU + (int)rank;                         // my half of the weight rows
+        const bool new_rp = RES && (rp != prev_rp);
+        for (int kb = 0; kb < ga.kb; ++kb) {
+          if (RES && new_rp) {
+            const uint32_t fb = smem_u32(&ctrl->a_full[kb]);
+            mbar_wait(smem_u32(&ctrl->a_empty[kb]), a_par ^ 1, ga.err, 1);
+            mbar_arrive_expect_tx(fb, TILE_BYTES);
+            bulk_g2s(a_smem + kb * TILE_BYTES, ga.A + ((size_t)rt * ga.kb + kb) * TILE_BYTES,
+                     TILE_BYTES, fb);
+          }
+          const uint32_t fb = smem_u32(&ctrl->ring_full[stage]);
+          mbar_wait(smem_u32(&ctrl->ring_empty[stage]), phase ^ 1, ga.err, 2);
+          if (ga.debug & 512) {
+            mbar_arrive(fb);
+          } else {
+            mbar_arrive_expect_tx(fb, STAGE_BYTES2);
+            uint32_t dst = ring_smem + stage * STAGE_BYTES2;
+            if (!RES) {
+              bulk_g2s(dst, ga.A + ((size_t)rt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
+              dst += TILE_BYTES;
+            }
+            bulk_g2s(dst, ga.B + ((size_t)nt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
+          }
+          if (++stage == ring_stages) { stage = 0; phase ^= 1; }
+        }
+        if (new_rp) { a_par ^= 1; prev_rp = rp; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 1) {
+      // ===================== forwarder (rank 1): my operands are in -> tell the leader ======
+      int stage = 0;
+      uint32_t phase = 0, a_par = 0;
+      int prev_rp = -1;
+      for (int u = u_begin; u < u_end; ++u) {
+        int rp, ng;
+        unit_coords(u, rp, ng);
+        const bool new_rp = RES && (rp != prev_rp);
+        for (int kb = 0; kb < ga.kb; ++kb) {
+          if (RES && new_rp) mbar_wait(smem_u32(&ctrl->a_full[kb]), a_par, ga.err, 9);
+          mbar_wait(smem_u32(&ctrl->ring_full[stage]), phase, ga.err, 10);
+          mbar_arrive_cluster(smem_u32(&ctrl->peer_full[stage]), 0);
+          if (++stage == ring_stages) { stage = 0; phase ^= 1; }
+        }
+        if (new_rp) { a_par ^= 1; prev_rp = rp; }
+      }
+    } else if (lane == 0) {
+      // ===================== MMA issuer (leader) =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * TILE_M, 2 * TILE_N);
+      int stage = 0;
+      uint32_t phase = 0, a_par = 0;
+      int prev_rp = -1;
+      int q = 0;  // 128-col tile sequence number (multiple of TU at unit start)
+      for (int u = u_begin; u < u_end; ++u) {
+        int rp, ng;
+        unit_coords(u, rp, ng);
+        const bool new_rp = RES && (rp != prev_rp);
+        bool last_of_rp = false;
+        if (RES) {
+          last_of_rp = true;
+          if (u + 1 < u_end) {
+            int rp2, ng2;
+            unit_coords(u + 1, rp2, ng2);
+            last_of_rp = rp2 != rp;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < TU; ++t)   // this unit's accumulator slots drained by both epilogues
+          mbar_wait(smem_u32(&ctrl->acc_empty[(q + t) & 3]), (((q + t) >> 2) & 1) ^ 1, ga.err, 4);
+        const uint32_t d = tmem_base + (uint32_t)((q & 3) * TILE_N);
+        for (int kb = 0; kb < ga.kb; ++kb) {
+          if (RES && new_rp) mbar_wait(smem_u32(&ctrl->a_full[kb]), a_par, ga.err, 5);
+          mbar_wait(smem_u32(&ctrl->ring_full[stage]), phase, ga.err, 7);
+          if (!(ga.debug & 256)) mbar_wait(smem_u32(&ctrl->peer_full[stage]), phase, ga.err, 11);
+          tc_fence_after();
+          const uint32_t s_base = ring_smem + stage * STAGE_BYTES2;
+          const uint32_t a_tile = RES ? a_smem + kb * TILE_BYTES : s_base;
+          const uint32_t b_tile = RES ? s_base : s_base + TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < TILE_K / 16; ++k) {
+            umma2_bf16(d, umma_desc_kmajor(a_tile + k * (2 * TILE_M * 16), TILE_M * 16),
+                       umma_desc_kmajor(b_tile + k * (2 * TILE_M * 16), TILE_M * 16), idesc,
+                       (kb | k) ? 1u : 0u);
+          }
+          umma2_commit_both(smem_u32(&ctrl->ring_empty[stage]));
+          if (last_of_rp) umma2_commit_both(smem_u32(&ctrl->a_empty[kb]));
+          if (++stage == ring_stages) { stage = 0; phase ^= 1; }
+        }
+#pragma unroll
+        for (int t = 0; t < TU; ++t) umma2_commit_both(smem_u32(&ctrl->acc_full[(q + t) & 3]));
+        q += TU;
+        if (new_rp) { a_par ^= 1; prev_rp = rp; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (two groups of 4 warps, both CTAs) =====================
+    const int eg = (warp - 4) >> 2;
+    const int lq = warp & 3;            // TMEM lane quadrant this warp may access
+    const int r = lq * 32 + lane;
+    const int n_local = (u_end - u_begin) * TU;
+    float* sb = ctrl->bias_stage[eg];
+    auto coords = [&](int q, int& rt, int& nt) {
+      int rp, ng;
+      unit_coords(u_begin + q / TU, rp, ng);
+      rt = 2 * rp + (int)rank;
+      nt = ng * TU + q % TU;
+    };
+    EpiState<EPI> st;
+    int rt = 0, nt = 0;
+    const bool skip = (ga.debug & 1) != 0;
+    if (eg < n_local && !skip) {
+      coords(eg, rt, nt);
+      if (rt < ga.row_tiles) epi_first<EPI>(ea, rt, nt, r, st);
+    }
+#pragma unroll 1
+    for (int q = eg; q < n_local; q += 2) {
+      coords(q, rt, nt);
+      const bool valid = rt < ga.row_tiles;                    // odd tail: rank 1 has no tile
+      int rt2 = rt, nt2 = nt;
+      bool valid2 = false;
+      if (q + 2 < n_local) {
+        coords(q + 2, rt2, nt2);
+        valid2 = rt2 < ga.row_tiles;
+      }
+      const int buf = q & 3, use = q >> 2;
+      if (valid && !skip) epi_stage_bias<EPI>(ea, sb, 1 + eg, r, st, valid2, nt2);
+      mbar_wait(smem_u32(&ctrl->acc_full[buf]), use & 1, ga.err, 8);
+      tc_fence_after();
+      const uint32_t tm = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
+      if (!skip) {
+        if (valid) epi_finish<EPI, ACT>(ea, tm, rt, nt, ga.n_tiles, r, sb, st, valid2, rt2, nt2);
+        else if (valid2) epi_first<EPI>(ea, rt2, nt2, r, st);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(smem_u32(&ctrl->acc_empty[buf]));
+        else mbar_arrive_cluster(smem_u32(&ctrl->acc_empty[buf]), 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer can still signal it
+  if (warp == 2) tmem_dealloc2(tmem_base, 512);
+}
+
+}  // namespace aid
