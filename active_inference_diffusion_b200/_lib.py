@@ -104,6 +104,14 @@ def _declare(l: ctypes.CDLL) -> None:
                              c_int32, c_int32, c_void_p, c_size_t, c_void_p]
 
 
+def _declare_train(l: ctypes.CDLL) -> None:
+    l.aid_gemm_nt_workspace_bytes.restype = c_size_t
+    l.aid_gemm_nt_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32]
+    l.aid_gemm_nt.restype = c_int32
+    l.aid_gemm_nt.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                              c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p]
+
+
 def lib() -> ctypes.CDLL:
     """Load the CUDA extension; fail loudly when it has not been built."""
     global _lib
@@ -114,6 +122,7 @@ def lib() -> ctypes.CDLL:
                 "g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
         l = ctypes.CDLL(LIB_PATH)
         _declare(l)
+        _declare_train(l)
         _lib = l
     return _lib
 
@@ -176,6 +185,42 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None, a
     check(l.aid_linear(ptr(x), ptr(w), ptr(b), ptr(y), M, N, K, act, int(via_packed), ptr(ws), ws_bytes,
                        stream_ptr(dev)), "aid_linear")
     return y
+
+
+def _strided_2d(t: torch.Tensor) -> torch.Tensor:
+    """fp32 2-D tensor with a unit stride in one dimension (transposed views are kept as views)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.stride(1) == 1 or t.stride(0) == 1:
+        return t
+    return t.contiguous()
+
+
+PRECISIONS = {"bf16": 0, "bf16x3": 1}
+
+
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None,
+            precision: str = "bf16") -> torch.Tensor:
+    """out[M,N] = a[M,K] @ b[N,K]^T (+ bias) on the tcgen05 path; a and b may be transposed views.
+    precision "bf16" rounds the operands to bf16; "bf16x3" uses the hi/lo split (fp32-class products)."""
+    prec = PRECISIONS[precision]
+    dev = require_cuda(a, b, bias)
+    a, b, bias = _strided_2d(a), _strided_2d(b), f32c(bias)
+    M, K = a.shape
+    N, K2 = b.shape
+    if K != K2:
+        raise ValueError(f"gemm_nt: inner dimensions differ ({K} vs {K2})")
+    out = torch.empty(M, N, dtype=torch.float32, device=dev)
+    if M == 0 or N == 0:
+        return out
+    if K == 0:
+        return out.zero_() if bias is None else out.copy_(bias.expand(M, N))
+    l = lib()
+    ws_bytes = l.aid_gemm_nt_workspace_bytes(M, N, K, prec)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(l.aid_gemm_nt(ptr(a), a.stride(0), a.stride(1), ptr(b), b.stride(0), b.stride(1), ptr(bias), ptr(out),
+                        M, N, K, prec, ptr(ws), ws_bytes, stream_ptr(dev)), "aid_gemm_nt")
+    return out
 
 
 def profile_select(epi: int, k: int = 0, n: int = 0) -> None:

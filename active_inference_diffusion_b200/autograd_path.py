@@ -1,11 +1,15 @@
-"""Differentiable torch-op evaluation of the score network, used ONLY to build the autograd graph
-of the training loss (`compute_diffusion_elbo`: backward and the gradient penalty's double
-backward, core/active_inference.py:584-606,709-729).
+"""Differentiable evaluation of the score network for the training loss
+(`compute_diffusion_elbo`: backward and the gradient penalty's double backward,
+core/active_inference.py:584-606,709-729).
 
-Status ("training path"): sampling, score forward and EFE run on the hand-written
-sm_100a kernels; the training loss still differentiates through these torch ops (cuBLAS on the
-device).  Native fwd/bwd kernels are SURVEY §8 row a9/a10, next round.  Nothing on the sampling or
-EFE path imports this module's `score_forward`.
+Every dense contraction of the graph -- forward x W^T, input gradient dY W, weight gradient
+dY^T X, and the same three again inside the double backward of the gradient penalty -- is
+`MatmulNT`, one autograd Function over the library's `aid_gemm_nt` (tcgen05, bf16 operands,
+fp32 accumulation, split-K for weight gradients).  Its backward is expressed with `MatmulNT`
+itself, so `create_graph=True` differentiates through it to any order without a second set of
+formulas.  The element-wise glue between the GEMMs (LayerNorm, SiLU/GELU, adaLN modulation,
+clamp) is memory-bound and stays on torch device ops, whose double-backward formulas autograd
+already has (DESIGN.md "training path").
 """
 from __future__ import annotations
 
@@ -14,6 +18,51 @@ from typing import Optional
 
 import torch
 import torch.nn.functional as F
+
+
+from . import _lib
+
+# Precision of the training-graph GEMMs: "bf16x3" (default; hi/lo operand split, products exact to
+# ~2^-16, meets the rel-1e-3 loss/gradient contract) or "bf16" (3x fewer tensor-core FLOPs;
+# measured gradient bound stated in DESIGN.md).
+PRECISION = "bf16x3"
+
+
+def set_precision(name: str) -> None:
+    global PRECISION
+    if name not in _lib.PRECISIONS:
+        raise ValueError(f"unknown precision {name!r}; expected one of {sorted(_lib.PRECISIONS)}")
+    PRECISION = name
+
+
+class MatmulNT(torch.autograd.Function):
+    """out[M,N] = a[M,K] @ b[N,K]^T through `aid_gemm_nt`.  d/da = g @ b, d/db = g^T @ a, both again
+    MatmulNT on transposed views, hence differentiable to any order."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return _lib.gemm_nt(a, b, precision=PRECISION)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ga = MatmulNT.apply(g, b.t()) if ctx.needs_input_grad[0] else None
+        gb = MatmulNT.apply(g.t(), a.t()) if ctx.needs_input_grad[1] else None
+        return ga, gb
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F.linear with the contraction on the tcgen05 path."""
+    y = MatmulNT.apply(x, weight)
+    return y if bias is None else y + bias
+
+
+def _seq(mods, x: torch.Tensor) -> torch.Tensor:
+    """nn.Sequential forward with every nn.Linear routed through `linear`."""
+    for m in mods:
+        x = linear(x, m.weight, m.bias) if isinstance(m, torch.nn.Linear) else m(x)
+    return x
 
 
 def _sinusoid(time: torch.Tensor, dim: int, freq_scale: torch.Tensor) -> torch.Tensor:
@@ -26,11 +75,12 @@ def _sinusoid(time: torch.Tensor, dim: int, freq_scale: torch.Tensor) -> torch.T
 
 def _time_embed(net, time: torch.Tensor) -> torch.Tensor:
     e = _sinusoid(time, net.time_embed_dim, net.time_embed[0].freq_scale)
-    return net.time_embed[3](F.silu(net.time_embed[1](e)))
+    t1, t3 = net.time_embed[1], net.time_embed[3]
+    return linear(F.silu(linear(e, t1.weight, t1.bias)), t3.weight, t3.bias)
 
 
 def _ada_ln(mod, x: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
-    scale, shift = mod.adaLN_modulation(cond).chunk(2, dim=-1)
+    scale, shift = _seq(mod.adaLN_modulation, cond).chunk(2, dim=-1)
     return F.layer_norm(x, (x.shape[-1],), None, None, 1e-5) * (1 + scale) + shift
 
 
@@ -41,26 +91,30 @@ def score_forward(net, z_t: torch.Tensor, time: torch.Tensor,
     H = net.hidden_dim
     continuous = bool(time.max() <= 1.0 and time.min() >= 0.0)
     if continuous:
-        t_emb = _time_embed(net, time * 999.0) + net.time_scale * net.continuous_time_embed(2.0 * time.view(-1, 1) - 1.0)
+        # continuous_time_embed.0 is Linear(1 -> E): an outer product, kept element-wise
+        c0 = net.continuous_time_embed[0]
+        t_norm = 2.0 * time.view(-1, 1) - 1.0
+        t_cont = _seq(list(net.continuous_time_embed)[1:], t_norm * c0.weight.view(1, -1) + c0.bias)
+        t_emb = _time_embed(net, time * 999.0) + net.time_scale * t_cont
         time_weight = torch.sqrt(1.0 / (1e-5 + time.view(-1, 1)))
     else:
         t_emb, time_weight = _time_embed(net, time), None
     if observation is not None:
         enc = net.obs_encoder
-        o = F.silu(enc[1](enc[0](observation)))
-        o = F.silu(enc[5](enc[4](o)))
-        o = enc[8](enc[7](o))
+        o = F.silu(enc[1](linear(observation, enc[0].weight, enc[0].bias)))
+        o = F.silu(enc[5](linear(o, enc[4].weight, enc[4].bias)))
+        o = enc[8](linear(o, enc[7].weight, enc[7].bias))
     else:
         o = torch.zeros(z_t.shape[0], H, device=z_t.device)
     cond = t_emb + o
-    h = net.latent_proj(z_t)
+    h = linear(z_t, net.latent_proj.weight, net.latent_proj.bias)
     for blk in net.transformer_blocks:
         att = blk.attention
         x = _ada_ln(blk.norm1, h, cond)
-        v = F.linear(x, att.in_proj_weight[2 * H:], att.in_proj_bias[2 * H:])   # seq-len-1 attention == out(V x)
-        h = h + att.out_proj(v)
-        h = h + blk.mlp(_ada_ln(blk.norm2, h, cond))
-    s = net.output_proj(_ada_ln(net.norm_final, h, cond))
+        v = linear(x, att.in_proj_weight[2 * H:], att.in_proj_bias[2 * H:])   # seq-len-1 attention == out(V x)
+        h = h + linear(v, att.out_proj.weight, att.out_proj.bias)
+        h = h + _seq(blk.mlp, _ada_ln(blk.norm2, h, cond))
+    s = _seq(net.output_proj, _ada_ln(net.norm_final, h, cond))
     s = torch.clamp(s, min=-10, max=10) * net.output_multiplier
     return s * time_weight if time_weight is not None else s
 

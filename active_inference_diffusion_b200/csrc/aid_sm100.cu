@@ -226,7 +226,7 @@ static int launch_gemm2_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t
 
 template <int EPI, int ACT>
 static int launch_gemm_shape(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t st, bool res, bool wide) {
-  if (use_pairs() && ga.n_tiles % 2 == 0) {
+  if (use_pairs() && ga.n_tiles % 2 == 0 && ga.splits == 1) {
     if (res) return launch_gemm2_inst<EPI, true, ACT>(ga, ea, st);
     return launch_gemm2_inst<EPI, false, ACT>(ga, ea, st);
   }
@@ -240,14 +240,17 @@ static int launch_gemm_shape(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t
 
 template <int EPI>
 static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs ea, cudaStream_t st,
-                       int* err_flag) {
+                       int* err_flag, int splits = 1) {
   GemmArgs ga;
   ga.A = A;
   ga.B = w.w;
   ga.row_tiles = row_tiles;
-  ga.kb = w.kb;
+  ga.kb = w.kb / splits;       // split-K: w.kb must be a multiple of splits
+  ga.kb_stride = w.kb;
+  ga.splits = splits;
   ga.n_tiles = w.n_tiles;
   ga.err = err_flag;
+  ea.split_rt = row_tiles;
   static const int dbg = getenv("AID_DEBUG") ? atoi(getenv("AID_DEBUG")) : 0;
   ga.debug = dbg;
   ea.debug = dbg;
@@ -257,7 +260,7 @@ static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs e
   static thread_local unsigned flip = 0;
   ga.reverse = (dbg & 8) ? 0 : (int)(flip++ & 1);
   if (!ea.bias) ea.bias = w.b;
-  const bool res = w.kb <= MAX_RES_KB;
+  const bool res = ga.kb <= MAX_RES_KB;
   const bool wide = w.nw == 2;   // N=256 MMAs whenever the tile count allows (fixed at pack time)
   // A resident in shared memory (K <= 512) or streamed through the ring.  Streamed A: one N=256
   // unit per pass so TMEM holds two units and the epilogue of unit u overlaps the MMAs of unit u+1
@@ -790,6 +793,128 @@ extern "C" int32_t aid_linear(const float* x, const float* wt, const float* bias
   } else {
     e.out_rm = y; e.ld_rm = N;
     AID_TRY(launch_gemm<EPI_F32>(reinterpret_cast<uint8_t*>(xp), rt, p, e, st, err));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// General strided GEMM for the training graph: out[M,N] = A[M,K] * B[N,K]^T (+ bias[N]).
+// Element (i,k) of A is a[i*a_rs + k*a_cs], likewise B, so forward (x W^T), dgrad (dY W) and
+// wgrad (dY^T X) are the same call with different strides.  Operands are rounded to bf16 when
+// packed; accumulation is fp32 in TMEM.
+// `triple` != 0 packs the bf16x3 split of the operand along K (three regions of kreg columns,
+// kreg = K rounded up to 64):  A side (1): [hi | hi | lo],  B side (2): [hi | lo | hi], with
+// hi = bf16(x), lo = bf16(x - hi).  One GEMM over 3*kreg columns then evaluates
+// hi*hi + hi*lo + lo*hi: the fp32 product to ~2^-16 relative, on the bf16 tensor pipe.
+__global__ void k_pack_strided(const float* __restrict__ src, long long rs, long long cs, int rows, int cols,
+                               __nv_bfloat16* __restrict__ dst, int row_tiles, int kb_total, int nw,
+                               int triple, int kreg) {
+  size_t total = (size_t)row_tiles * kb_total * 1024;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    int rt, kb, r, ch;
+    chunk_coords(idx, kb_total, rt, kb, r, ch);
+    const int row = rt * TILE_M + r;
+    int c0 = kb * TILE_K + ch * 8;
+    int want_lo = 0;
+    if (triple) {
+      const int region = c0 / kreg;
+      c0 -= region * kreg;
+      want_lo = (triple == 1) ? (region == 2) : (region == 1);
+    }
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float x = (row < rows && c0 + i < cols) ? __ldg(src + (long long)row * rs + (long long)(c0 + i) * cs) : 0.f;
+      if (want_lo) x -= __bfloat162float(__float2bfloat16_rn(x));
+      v[i] = x;
+    }
+    store_chunk(dst, rt, kb, kb_total, r, ch, v, nw);
+  }
+}
+
+// out[m, n] = sum_s partial[s][m][n] (+ bias[n]); partial rows are padded to m_pad per split
+__global__ void k_sum_splits(const float* __restrict__ partial, int splits, int m_pad, int M, int N,
+                             const float* __restrict__ bias, float* __restrict__ out) {
+  const size_t total = (size_t)M * N;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / N), n = (int)(idx % N);
+    float acc = bias ? __ldg(bias + n) : 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * m_pad + m) * N + n];
+    out[idx] = acc;
+  }
+}
+
+static int gemm_nt_splits(int M, int N, int K) {
+  // long reductions with few output tiles (weight gradients): spread the K range over the SMs
+  const int units = ceil_div(M, TILE_M) * ceil_div(ceil_div(N, TILE_N), 2);
+  const int kb = ceil_div(K, TILE_K);
+  int s = 1;
+  while (units * s * 2 <= num_sms() + num_sms() / 2 && kb % (s * 2) == 0 && kb / (s * 2) >= 16) s *= 2;
+  return s;
+}
+
+struct GemmNtLayout {
+  PLin p;
+  int rt, splits;
+  int* err;
+  __nv_bfloat16* ap;
+  float* partial;
+  size_t total;
+};
+static void gemm_nt_layout(int M, int N, int K, int precision, void* ws, GemmNtLayout& g) {
+  Arena a(ws);
+  const int kreg = ceil_div(K, TILE_K) * TILE_K;
+  const int keff = precision ? 3 * kreg : K;
+  plin_shape(g.p, N, keff);
+  g.rt = ceil_div(M, TILE_M);
+  g.splits = gemm_nt_splits(M, N, keff);
+  g.err = a.take<int>(1024);
+  g.ap = a.take<__nv_bfloat16>(packed_tiles_bytes(M, keff));
+  g.p.w = a.take<uint8_t>(plin_w_bytes(g.p));
+  g.p.b = a.take<float>(plin_b_bytes(g.p));
+  g.partial = g.splits > 1 ? a.take<float>((size_t)g.splits * g.rt * TILE_M * N * sizeof(float)) : nullptr;
+  g.total = align_up(a.off, 1024);
+}
+
+extern "C" size_t aid_gemm_nt_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t precision) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  GemmNtLayout g;
+  gemm_nt_layout(M, N, K, precision, nullptr, g);
+  return g.total;
+}
+
+extern "C" int32_t aid_gemm_nt(const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs,
+                               int64_t b_cs, const float* bias, float* out, int32_t M, int32_t N, int32_t K,
+                               int32_t precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!a || !b || !out || !workspace) return fail("aid_gemm_nt: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0) return fail("aid_gemm_nt: bad shape");
+  GemmNtLayout g;
+  gemm_nt_layout(M, N, K, precision, workspace, g);
+  if (workspace_bytes < g.total) return fail("aid_gemm_nt: workspace too small");
+  const int kreg = ceil_div(K, TILE_K) * TILE_K;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AID_CHECK(cudaMemsetAsync(g.err, 0, sizeof(int), st));
+  k_pack_strided<<<ew_grid((size_t)g.rt * g.p.kb * 1024), 256, 0, st>>>(a, a_rs, a_cs, M, K, g.ap, g.rt, g.p.kb, 1,
+                                                                         precision ? 1 : 0, kreg);
+  AID_LAUNCH_CHECK("k_pack_strided(a)");
+  k_pack_strided<<<ew_grid((size_t)g.p.n_tiles * g.p.kb * 1024), 256, 0, st>>>(
+      b, b_rs, b_cs, N, K, reinterpret_cast<__nv_bfloat16*>(const_cast<uint8_t*>(g.p.w)), g.p.n_tiles, g.p.kb, g.p.nw,
+      precision ? 2 : 0, kreg);
+  AID_LAUNCH_CHECK("k_pack_strided(b)");
+  const int n_pad = g.p.n_tiles * TILE_N;
+  const bool direct = g.splits == 1;
+  k_pack_bias<<<ceil_div(n_pad, 256), 256, 0, st>>>(direct ? bias : nullptr, direct && bias ? N : 0,
+                                                   const_cast<float*>(g.p.b), n_pad, MAP_PLAIN, 0);
+  AID_LAUNCH_CHECK("k_pack_bias");
+  EpiArgs e = epi_zero();
+  e.n_valid = N; e.rows_valid = M; e.ld_rm = N;
+  e.out_rm = direct ? out : g.partial;
+  AID_TRY(launch_gemm<EPI_F32>(reinterpret_cast<uint8_t*>(g.ap), g.rt, g.p, e, st, g.err, g.splits));
+  if (!direct) {
+    k_sum_splits<<<ew_grid((size_t)M * N), 256, 0, st>>>(g.partial, g.splits, g.rt * TILE_M, M, N, bias, out);
+    AID_LAUNCH_CHECK("k_sum_splits");
   }
   return 0;
 }

@@ -182,10 +182,19 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
           __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + (n0 >> 6)) * TILE_ELEMS;
           store_packed32(tile, r, n0 & 63, yp);
         }
-        if (e.out_rm && row < e.rows_valid) {
+        if (e.out_rm && (rt % e.split_rt) * TILE_M + r < e.rows_valid) {
+          // split-K: rt = split * split_rt + row tile; every split owns a block of split_rt*128 rows
+          float* orow = e.out_rm + (size_t)row * e.ld_rm + n0;
+          if (n0 + 32 <= e.n_valid && (e.ld_rm & 3) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < e.n_valid) e.out_rm[(size_t)row * e.ld_rm + n0 + j] = y[j];
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(orow + q * 4) =
+                  make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < e.n_valid) orow[j] = y[j];
+          }
         }
         if (e.stats_out) {
           int nv = min(32, max(0, e.n_valid - n0));

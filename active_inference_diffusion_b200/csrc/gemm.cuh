@@ -51,8 +51,11 @@ struct GemmArgs {
   const uint8_t* A;  // packed
   const uint8_t* B;  // packed
   int row_tiles;
-  int kb;       // K / 64
+  int kb;       // K / 64 processed per unit (per split)
   int n_tiles;  // N_pad / 128
+  int kb_stride;  // k-blocks per row tile in memory (= kb * splits)
+  int splits;     // split-K: unit = (split, row tile, column group); split s reduces k-blocks
+                  // [s*kb, (s+1)*kb) and stores to row block s of the (row-major) output
   int* err;
   int reverse;  // walk the units in descending order (see launch_gemm: L2 reuse between kernels)
   int debug;    // developer knobs (AID_DEBUG env): 1 = skip epilogue math, 2 = skip B loads
@@ -75,6 +78,7 @@ struct EpiArgs {
   float2* stats_out;         // may be null; [rt][n_tiles][128]
   float* out_rm;             // optional row-major output [rows_valid, ld_rm]
   int ld_rm;
+  int split_rt;              // row tiles per split (= row_tiles); out_rm row = rt*128 + r over all splits
   // EPI_MODLN
   const float4* h_tiled;     // [rt][h_ld4][128]
   int h_ld4;
@@ -210,7 +214,7 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int groups = ga.n_tiles / TU;  // units per row tile
-  const int num_units = ga.row_tiles * groups;
+  const int num_units = ga.splits * ga.row_tiles * groups;
   const int u_begin = (int)((long long)blockIdx.x * num_units / gridDim.x);
   const int u_end = (int)((long long)(blockIdx.x + 1) * num_units / gridDim.x);
 
@@ -247,7 +251,9 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       int prev_rt = -1;
       for (int u = u_begin; u < u_end; ++u) {
         const int ue = ga.reverse ? num_units - 1 - u : u;
-        const int rt = ue / groups, ng = ue % groups;
+        const int rt = ue / groups, ng = ue % groups;   // rt counts (split, row tile) pairs
+        const size_t a_row = (size_t)(rt % ga.row_tiles) * ga.kb_stride + (size_t)(rt / ga.row_tiles) * ga.kb;
+        const size_t kb_split = (size_t)(rt / ga.row_tiles) * ga.kb;
         const bool new_rt = RES && (rt != prev_rt);
         for (int kb = 0; kb < ga.kb; ++kb) {
           if (RES) {
@@ -255,15 +261,13 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
               const uint32_t fb = smem_u32(&ctrl->a_full[kb]);
               mbar_wait(smem_u32(&ctrl->a_empty[kb]), a_par ^ 1, ga.err, 1);
               mbar_arrive_expect_tx(fb, TILE_BYTES);
-              bulk_g2s(a_smem + kb * TILE_BYTES,
-                       ga.A + ((size_t)rt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
+              bulk_g2s(a_smem + kb * TILE_BYTES, ga.A + (a_row + kb) * TILE_BYTES, TILE_BYTES, fb);
             }
           } else {
             const uint32_t fb = smem_u32(&ctrl->ring_full[stage]);
             mbar_wait(smem_u32(&ctrl->ring_empty[stage]), phase ^ 1, ga.err, 2);
             mbar_arrive_expect_tx(fb, TILE_BYTES);
-            bulk_g2s(ring_smem + stage * SLOT_BYTES,
-                     ga.A + ((size_t)rt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
+            bulk_g2s(ring_smem + stage * SLOT_BYTES, ga.A + (a_row + kb) * TILE_BYTES, TILE_BYTES, fb);
             if (++stage == ring_stages) { stage = 0; phase ^= 1; }
           }
 #pragma unroll
@@ -275,7 +279,8 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
             } else {
               mbar_arrive_expect_tx(fb, SLOT_BYTES);   // weight tiles are packed NW*128 rows tall
               bulk_g2s(ring_smem + stage * SLOT_BYTES,
-                       ga.B + ((size_t)(ng * G + g) * ga.kb + kb) * SLOT_BYTES, SLOT_BYTES, fb);
+                       ga.B + ((size_t)(ng * G + g) * ga.kb_stride + kb_split + kb) * SLOT_BYTES,
+                       SLOT_BYTES, fb);
             }
             if (++stage == ring_stages) { stage = 0; phase ^= 1; }
           }
@@ -349,7 +354,7 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
     const int r = lq * 32 + lane;
     const int n_local = (u_end - u_begin) * TU;
     float* sb = ctrl->bias_stage[eg];
-    auto coords = [&](int q, int& rt, int& nt) {
+    auto coords = [&](int q, int& rt, int& nt) {   // rt counts (split, row tile) pairs
       const int u = u_begin + q / TU;
       const int ue = ga.reverse ? num_units - 1 - u : u;
       rt = ue / groups;

@@ -210,6 +210,21 @@ int32_t aid_linear(const float* x, const float* w, const float* bias, float* y, 
                    int32_t N, int32_t K, int32_t act, int32_t via_packed, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* ---- training graph GEMM: out[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) ---------------------------
+ * Replaces the cuBLAS calls behind every nn.Linear / F.linear of the score network inside
+ * compute_diffusion_elbo and its backward / double backward (core/active_inference.py:584-606,
+ * 709-729; models/score_networks.py:41-99,189-202).  Element (i,k) of A is a[i*a_rs + k*a_cs]
+ * (same for B), so x W^T (forward), dY W (input gradient) and dY^T X (weight gradient) are one
+ * entry point.  fp32 in / fp32 out, bf16 tensor-core operands, fp32 accumulation; long reductions
+ * with few output tiles are split over K internally.
+ * precision: 0 = bf16 operands (error ~2^-9 per product);  1 = bf16x3: each operand split into
+ * hi + lo bf16 halves and hi*hi + hi*lo + lo*hi accumulated in one GEMM of 3x the reduction
+ * length -- products exact to ~2^-16, the mode that meets the rel-1e-3 gradient contract. */
+size_t aid_gemm_nt_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t precision);
+int32_t aid_gemm_nt(const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs,
+                    int64_t b_cs, const float* bias, float* out, int32_t M, int32_t N, int32_t K,
+                    int32_t precision, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,7 +127,12 @@ def test_update_belief_via_diffusion_matches_oracle():
     assert abs(float(out["reconstruction_error"]) - float(rec)) < 2e-2 * float(rec)
 
 
-def test_diffusion_elbo_loss_and_grads_fp32():
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-3), ("bf16", 3e-2)])
+def test_diffusion_elbo_loss_and_grads(precision, tol):
+    """-ELBO, its info terms and every score-net / diffusion gradient (incl. the gradient
+    penalty's double backward) vs the oracle.  bf16x3 (default) meets the rel-1e-3 contract;
+    bf16 is the fast mode with the separately stated bound (precision)."""
+    from active_inference_diffusion_b200 import autograd_path as AP
     L, A, H, B = 32, 6, 128, 24
     ai, nets, cfg = make_ai(L, A, H)
     g = gen(21)
@@ -138,30 +143,35 @@ def test_diffusion_elbo_loss_and_grads_fp32():
     n1 = torch.randn(B, L, generator=g)
     n2 = torch.randn(B, L, generator=g)
     prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False     # decoder / reward heads (not on the score path)
+    AP.set_precision(precision)
     try:
         loss, info = ai.compute_diffusion_elbo(obs.cuda(), rew.cuda(), lat.cuda(), t=t.cuda(), noise=n1.cuda(),
                                                prior_eps=n2.cuda())
         loss.backward()
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+        AP.set_precision("bf16x3")
     sp = {k: v.clone().requires_grad_(True) for k, v in nets["score"].items() if v.is_floating_point()}
     dp = {k: nets["diffusion"][k].clone().requires_grad_(True)
           for k in ("latent_prior_mean", "latent_prior_log_std", "log_snr_min", "log_snr_max")}
     ecfg = dict(kl_weight=cfg.kl_weight, diffusion_weight=cfg.diffusion_weight, reward_weight=cfg.reward_weight)
     want, winfo, per = R.diffusion_elbo(sp, dp, nets["decoder"], nets["reward"], ecfg, obs, rew, lat, t, n1, n2)
     want.backward()
-    assert abs(float(loss) - float(want)) < 1e-3 * abs(float(want))
+    assert abs(float(loss) - float(want)) < tol * abs(float(want))
     for k in ("score_matching_loss", "grad_penalty", "kl_loss", "reward_loss", "reconstruction_loss"):
-        assert abs(info[k] - float(winfo[k])) < 1e-3 * (abs(float(winfo[k])) + 1e-6), k
+        assert abs(info[k] - float(winfo[k])) < tol * (abs(float(winfo[k])) + 1e-6), k
+    worst = 0.0
     for k, p in ai.latent_score_network.named_parameters():
         if p.grad is None:
             continue
-        assert rel_l2(p.grad, sp[k].grad) < 1e-3, (k, rel_l2(p.grad, sp[k].grad))
+        worst = max(worst, rel_l2(p.grad, sp[k].grad))
+        assert rel_l2(p.grad, sp[k].grad) < tol, (k, rel_l2(p.grad, sp[k].grad))
     for k, p in ai.latent_diffusion.named_parameters():
         if p.grad is not None:
-            assert rel_l2(p.grad, dp[k].grad) < 1e-3, k
+            assert rel_l2(p.grad, dp[k].grad) < tol, k
+    print(f"elbo[{precision}]: worst score-net gradient rel-L2 = {worst:.2e}")
     # time-importance bins are integer work: exact
     w = R.update_time_importance(torch.ones(100), t, per.detach())
-    assert torch.allclose(ai.time_importance_weights.cpu(), w, rtol=1e-3, atol=1e-6)
+    assert torch.allclose(ai.time_importance_weights.cpu(), w, rtol=tol, atol=1e-6)
     assert torch.equal((t.cuda() * 99).long().clamp(0, 99).cpu(), R.time_importance_bins(t))
