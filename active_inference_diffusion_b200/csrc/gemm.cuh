@@ -245,6 +245,10 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
+      // L2 policy: weight tiles are read by every CTA and a streamed A row tile is read again by
+      // the next unit of the same CTA -> keep (evict_last); a resident A tile is read once ->
+      // evict_first (ncu showed mlp.2 re-reading its 268 MB A operand from DRAM on the second pass).
+      const uint64_t keep = policy_evict_last(), once = policy_evict_first();
       int stage = 0;
       uint32_t phase = 0;
       uint32_t a_par = 0;
@@ -261,13 +265,14 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
               const uint32_t fb = smem_u32(&ctrl->a_full[kb]);
               mbar_wait(smem_u32(&ctrl->a_empty[kb]), a_par ^ 1, ga.err, 1);
               mbar_arrive_expect_tx(fb, TILE_BYTES);
-              bulk_g2s(a_smem + kb * TILE_BYTES, ga.A + (a_row + kb) * TILE_BYTES, TILE_BYTES, fb);
+              bulk_g2s_hint(a_smem + kb * TILE_BYTES, ga.A + (a_row + kb) * TILE_BYTES, TILE_BYTES, fb, once);
             }
           } else {
             const uint32_t fb = smem_u32(&ctrl->ring_full[stage]);
             mbar_wait(smem_u32(&ctrl->ring_empty[stage]), phase ^ 1, ga.err, 2);
             mbar_arrive_expect_tx(fb, TILE_BYTES);
-            bulk_g2s(ring_smem + stage * SLOT_BYTES, ga.A + (a_row + kb) * TILE_BYTES, TILE_BYTES, fb);
+            bulk_g2s_hint(ring_smem + stage * SLOT_BYTES, ga.A + (a_row + kb) * TILE_BYTES, TILE_BYTES, fb,
+                          (ga.debug & 8) ? once : keep);
             if (++stage == ring_stages) { stage = 0; phase ^= 1; }
           }
 #pragma unroll
@@ -278,9 +283,9 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
               mbar_arrive(fb);
             } else {
               mbar_arrive_expect_tx(fb, SLOT_BYTES);   // weight tiles are packed NW*128 rows tall
-              bulk_g2s(ring_smem + stage * SLOT_BYTES,
-                       ga.B + ((size_t)(ng * G + g) * ga.kb_stride + kb_split + kb) * SLOT_BYTES,
-                       SLOT_BYTES, fb);
+              bulk_g2s_hint(ring_smem + stage * SLOT_BYTES,
+                            ga.B + ((size_t)(ng * G + g) * ga.kb_stride + kb_split + kb) * SLOT_BYTES,
+                            SLOT_BYTES, fb, keep);
             }
             if (++stage == ring_stages) { stage = 0; phase ^= 1; }
           }

@@ -164,9 +164,15 @@ class LatentScoreNetwork(nn.Module):
         if not self.use_attention:
             raise NotImplementedError("use_attention=False is never instantiated by the reference")
         dev = _lib.require_cuda(z_t, time, observation)
-        if torch.is_grad_enabled() and (z_t.requires_grad or any(p.requires_grad for p in self.parameters())):
-            # inference entry point; the training path goes through ops.dsm_loss
-            z_t = z_t.detach()
+        if torch.is_grad_enabled() and (z_t.requires_grad or time.requires_grad
+                                        or (observation is not None and observation.requires_grad)
+                                        or any(p.requires_grad for p in self.parameters())):
+            # A caller that records a graph (the reference's own compute_diffusion_elbo :584,717, or
+            # FreeEnergyComputation :77) gets the differentiable evaluation: same math, every GEMM on
+            # aid_gemm_nt, differentiable to any order.  Under torch.no_grad() the fused inference
+            # kernels below run.
+            from . import autograd_path
+            return autograd_path.score_forward(self, _lib.f32c(z_t), _lib.f32c(time), _lib.f32c(observation))
         z_t, time, observation = _lib.f32c(z_t), _lib.f32c(time), _lib.f32c(observation)
         batch = z_t.shape[0]
         continuous = bool(time.max() <= 1.0 and time.min() >= 0.0)

@@ -225,7 +225,7 @@ def run_ours(args):
     barrier()
 
     # --- timed region (device-resident inputs); dominant-kernel events + clocks sampled inside it
-    _lib.profile_select(1, 4 * H, H)          # FC2: mlp.2, K=4H, N=H, residual + LayerNorm partials epilogue
+    _lib.profile_select(0, H, 4 * H)          # mlp.0: K=H, N=4H, bias + GELU -> packed bf16 epilogue
     _lib.reset_launch_count()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -255,8 +255,8 @@ def run_ours(args):
     if rank == 0:
         peaks = measured_peaks()
         per_launch_ms = k_ms / max(k_n, 1)
-        fc2_flops = 2.0 * CANDIDATES * (4 * H) * H
-        achieved = fc2_flops / (per_launch_ms * 1e-3) / 1e12 if k_n else None
+        fc1_flops = 2.0 * CANDIDATES * H * (4 * H)
+        achieved = fc1_flops / (per_launch_ms * 1e-3) / 1e12 if k_n else None
         peak = peaks["sustained"] or peaks["burst"]
         step_tflops = F_CANDIDATE * CANDIDATES / (ms_step * 1e-3) / 1e12
         out = {
@@ -276,11 +276,11 @@ def run_ours(args):
                     "h2d_bytes_per_step": CANDIDATES * O * 4 * world, "d2h_bytes_per_step": CANDIDATES * (1 + A) * 4 * world},
             "gpu_launches": int(launches),
             "roofline": {
-                "bound": "tensor", "kernel": "gemm_kernel<EPI_F32,NW=2,G=2,streamed A> (mlp.2: [65536x2048]x[2048x512] + residual + LN partials)",
+                "bound": "tensor", "kernel": "gemm_kernel<EPI_PACK,NW=2,G=1,resident A,GELU> (mlp.0: [65536x512]x[512x2048] + bias + GELU -> packed bf16; largest share of the step's FLOPs)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); burst figure {peaks['burst']}",
-                "launches_timed": k_n, "avg_launch_ms": per_launch_ms, "flops_per_launch": fc2_flops,
-                "traffic": 508.3e6, "traffic_note": "dram bytes r+w per launch from profiles/r1_ncu_full_gemm_kernels.csv",
+                "launches_timed": k_n, "avg_launch_ms": per_launch_ms, "flops_per_launch": fc1_flops,
+                "traffic": 296.9e6, "traffic_note": "dram bytes read+written per launch (86.0 + 210.9 MB) from profiles/r1_ncu_full_gemm_kernels_v2.csv; algorithmic: 67 MB packed A in + 268 MB packed activations out",
                 "whole_step_tflops": step_tflops, "whole_step_frac_of_peak": step_tflops / peak},
             "cpu_baseline": cb,
         }
