@@ -171,6 +171,17 @@ class DiffusionActiveInference(nn.Module):
         self.epistemic_estimator.device = device
         return self
 
+    def _apply(self, fn, *args, **kwargs):
+        # .cuda() / .cpu() / .to() all funnel through _apply: keep `self.device` (used like the
+        # reference's `config.device`, core/active_inference.py:44) in step with the parameters
+        out = super()._apply(fn, *args, **kwargs)
+        p = next(self.parameters(), None)
+        if p is not None:
+            self.device = p.device
+            if hasattr(self, "epistemic_estimator"):
+                self.epistemic_estimator.device = p.device
+        return out
+
     # ---- small heads ---------------------------------------------------------------------
     def decode_observation(self, latent: torch.Tensor, decode_to_pixels: bool = True) -> torch.Tensor:
         latent = latent.to(self.device)

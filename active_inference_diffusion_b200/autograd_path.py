@@ -52,10 +52,28 @@ class MatmulNT(torch.autograd.Function):
         return ga, gb
 
 
+class LinearNT(torch.autograd.Function):
+    """x W^T + b with the bias added in the GEMM epilogue; gradients again through MatmulNT."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return _lib.gemm_nt(x, weight, bias, precision=PRECISION)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        gx = MatmulNT.apply(g, weight.t()) if ctx.needs_input_grad[0] else None
+        gw = MatmulNT.apply(g.t(), x.t()) if ctx.needs_input_grad[1] else None
+        gb = g.sum(0) if ctx.needs_input_grad[2] else None
+        return gx, gw, gb
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """F.linear with the contraction on the tcgen05 path."""
-    y = MatmulNT.apply(x, weight)
-    return y if bias is None else y + bias
+    """F.linear with the contraction (and the bias add) on the tcgen05 path."""
+    if bias is None:
+        return MatmulNT.apply(x, weight)
+    return LinearNT.apply(x, weight, bias)
 
 
 def _seq(mods, x: torch.Tensor) -> torch.Tensor:

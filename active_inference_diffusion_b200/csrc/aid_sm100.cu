@@ -814,6 +814,10 @@ __global__ void k_pack_strided(const float* __restrict__ src, long long rs, long
        idx += (size_t)gridDim.x * blockDim.x) {
     int rt, kb, r, ch;
     chunk_coords(idx, kb_total, rt, kb, r, ch);
+    if (cs == 1) {   // row-major source: neighbouring lanes take neighbouring 32-byte pieces of one row
+      ch = (int)(idx & 7);
+      r = (int)((idx >> 3) & 127);
+    }
     const int row = rt * TILE_M + r;
     int c0 = kb * TILE_K + ch * 8;
     int want_lo = 0;
