@@ -35,8 +35,10 @@ class FunctionSpaceEpistemicEstimator(nn.Module):
     """State-mode MINE epistemic estimator (core/active_inference.py:839-1063), parameters and
     forward.  The reference forward calls `self.decoder(z)` on an nn.ModuleList, which raises
     (:953); here the decoder is applied with `decode_observation`'s skip forward (:237-242), the
-    documented shim of SURVEY §8c(1).  Runs with torch ops on the device (not on the sampling
-    hot path; it yields ONE scalar per call for the whole batch, :1050-1053)."""
+    documented shim of SURVEY §8c(1).  All its dense layers (decoder x5 passes, feature extractor,
+    projector, latent processor, MINE network) run on `aid_gemm_nt` in the bf16x3 mode: the value is
+    a difference of two batch means, so it is kept at fp32-class precision.  It yields ONE scalar
+    per call for the whole batch (:1050-1053)."""
 
     def __init__(self, decoder: nn.Module, latent_dim: int, observation_shape, hidden_dim: int = 256,
                  spatial_aggregator_output_dim: int = 256, is_pixel_observation: bool = True,
@@ -69,39 +71,46 @@ class FunctionSpaceEpistemicEstimator(nn.Module):
         self.device = device if isinstance(device, torch.device) else torch.device(device)
         return self
 
+    # Every nn.Linear below runs through autograd_path.seq -> aid_gemm_nt (tcgen05); LayerNorm /
+    # ReLU / SiLU / Dropout(eval) stay element-wise device ops.
     def _decode(self, z: torch.Tensor) -> torch.Tensor:
         m = self.decoder
-        h1 = m[0](z)
-        h2 = m[1](h1) + h1
-        return m[3](m[2](h2))
+        h1 = autograd_path.seq(m[0], z)
+        h2 = autograd_path.seq(m[1], h1) + h1
+        return autograd_path.linear(autograd_path.seq(m[2], h2), m[3].weight, m[3].bias)
 
-    def compute_jacobian_features(self, z: torch.Tensor) -> torch.Tensor:
+    def compute_jacobian_features(self, z: torch.Tensor, dir_noise=None) -> torch.Tensor:
         was_training = self.decoder.training
         self.decoder.eval()
         with torch.no_grad():
             f_z = self._decode(z)
         eps = self.perturbation_scale
         feats = []
-        for _ in range(self.ntk_samples):
-            delta = F.normalize(torch.randn_like(z), dim=-1) * eps
+        for i in range(self.ntk_samples):
+            d = torch.randn_like(z) if dir_noise is None else dir_noise[i]
+            delta = F.normalize(d, dim=-1) * eps
             with torch.no_grad():
                 f_p = self._decode(z + delta)
-            feats.append(self.feature_extractor((f_p - f_z) / eps))
+            feats.append(autograd_path.seq(self.feature_extractor, (f_p - f_z) / eps))
         if was_training:
             self.decoder.train()
-        return self.jacobian_projector(torch.cat(feats, dim=1))
+        return autograd_path.seq(self.jacobian_projector, torch.cat(feats, dim=1))
 
-    def forward(self, next_latent_mean: torch.Tensor, next_latent_logvar: torch.Tensor, num_samples: int = 5):
+    def forward(self, next_latent_mean: torch.Tensor, next_latent_logvar: torch.Tensor, num_samples: int = 5,
+                *, z_noise=None, dir_noise=None, perms=None):
+        """Keyword-only arguments inject the reference's draws in its order: S x
+        randn_like [B,L], 4 x randn_like [S*B,L], S x randperm(B)."""
         B = next_latent_mean.shape[0]
-        zs = [next_latent_mean + torch.randn_like(next_latent_mean) * torch.exp(0.5 * next_latent_logvar)
-              for _ in range(num_samples)]
+        std = torch.exp(0.5 * next_latent_logvar)
+        zs = [next_latent_mean + (torch.randn_like(next_latent_mean) if z_noise is None else z_noise[i]) * std
+              for i in range(num_samples)]
         z_all = torch.cat(zs, dim=0)
-        jac = self.compute_jacobian_features(z_all)
-        lat = self.latent_processor(z_all)
-        t_joint = self.mine_network(torch.cat([jac, lat], dim=1))
-        marg = torch.cat([jac[i * B:(i + 1) * B][torch.randperm(B, device=jac.device)]
+        jac = self.compute_jacobian_features(z_all, dir_noise)
+        lat = autograd_path.seq(self.latent_processor, z_all)
+        t_joint = autograd_path.seq(self.mine_network, torch.cat([jac, lat], dim=1))
+        marg = torch.cat([jac[i * B:(i + 1) * B][torch.randperm(B, device=jac.device) if perms is None else perms[i]]
                           for i in range(num_samples)], dim=0)
-        t_marg = self.mine_network(torch.cat([marg, lat], dim=1))
+        t_marg = autograd_path.seq(self.mine_network, torch.cat([marg, lat], dim=1))
         # ema_loss (:828-836): forward value log(mean(exp(T))), running mean updated on the side
         t_exp = torch.exp(torch.logsumexp(t_marg, 0) - math.log(t_marg.shape[0])).detach()
         if float(self.running_mean) == 0:
@@ -186,9 +195,9 @@ class DiffusionActiveInference(nn.Module):
     def decode_observation(self, latent: torch.Tensor, decode_to_pixels: bool = True) -> torch.Tensor:
         latent = latent.to(self.device)
         m = self.observation_decoder
-        h1 = m[0](latent)
-        h2 = m[1](h1) + h1
-        return m[3](m[2](h2))
+        h1 = autograd_path.seq(m[0], latent)
+        h2 = autograd_path.seq(m[1], h1) + h1
+        return autograd_path.linear(autograd_path.seq(m[2], h2), m[3].weight, m[3].bias)
 
     def predict_reward_from_latent(self, latent: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         out = self._heads.head_forward(3, latent.to(self.device))
@@ -350,7 +359,7 @@ class DiffusionActiveInference(nn.Module):
             prior = diff.latent_prior_mean.unsqueeze(0) + torch.exp(diff.latent_prior_log_std).unsqueeze(0) * prior_eps
         kl = self._compute_latent_kl(latents, prior).mean()
         klw = torch.exp(-5.0 * t.mean())
-        pr = self.reward_predictor(latents)
+        pr = autograd_path.seq(self.reward_predictor, latents)
         r_std = torch.exp(torch.clamp(pr[:, 1], min=-5, max=2))
         rl = -torch.distributions.Normal(pr[:, 0], r_std).log_prob(rewards).mean()
         c = self.config

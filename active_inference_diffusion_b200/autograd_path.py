@@ -28,6 +28,23 @@ from . import _lib
 PRECISION = "bf16x3"
 
 
+class precision:
+    """`with precision("bf16"):` — GEMM precision for a region (e.g. inference-only estimators)."""
+
+    def __init__(self, name: str):
+        if name not in _lib.PRECISIONS:
+            raise ValueError(f"unknown precision {name!r}")
+        self.name = name
+
+    def __enter__(self):
+        global PRECISION
+        self.prev, PRECISION = PRECISION, self.name
+
+    def __exit__(self, *exc):
+        global PRECISION
+        PRECISION = self.prev
+
+
 def set_precision(name: str) -> None:
     global PRECISION
     if name not in _lib.PRECISIONS:
@@ -77,10 +94,18 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
 
 
 def _seq(mods, x: torch.Tensor) -> torch.Tensor:
-    """nn.Sequential forward with every nn.Linear routed through `linear`."""
+    """nn.Sequential forward with every nn.Linear routed through `linear` (nested Sequentials too)."""
     for m in mods:
-        x = linear(x, m.weight, m.bias) if isinstance(m, torch.nn.Linear) else m(x)
+        if isinstance(m, torch.nn.Linear):
+            x = linear(x, m.weight, m.bias)
+        elif isinstance(m, torch.nn.Sequential):
+            x = _seq(m, x)
+        else:
+            x = m(x)
     return x
+
+
+seq = _seq
 
 
 def _sinusoid(time: torch.Tensor, dim: int, freq_scale: torch.Tensor) -> torch.Tensor:

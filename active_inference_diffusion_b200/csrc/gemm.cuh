@@ -215,8 +215,19 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
   const int lane = threadIdx.x & 31;
   const int groups = ga.n_tiles / TU;  // units per row tile
   const int num_units = ga.splits * ga.row_tiles * groups;
-  const int u_begin = (int)((long long)blockIdx.x * num_units / gridDim.x);
-  const int u_end = (int)((long long)(blockIdx.x + 1) * num_units / gridDim.x);
+  // RES: a contiguous range of units per CTA, so the resident A row tile serves all its column
+  // groups.  Streamed A: units are dealt round-robin, so the column groups of one row tile run at
+  // the same time on neighbouring CTAs and the second read of the A tile hits L2 (with contiguous
+  // ranges ncu showed mlp.2 pulling its 268 MB A operand from DRAM twice).
+  const int u_lo = (int)((long long)blockIdx.x * num_units / gridDim.x);
+  const int u_hi = (int)((long long)(blockIdx.x + 1) * num_units / gridDim.x);
+  const int u_begin = 0;
+  const int u_end = RES ? u_hi - u_lo
+                        : (num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto unit_at = [&](int i) {   // i-th unit of this CTA -> global unit index (before reversal)
+    const int u = RES ? u_lo + i : (int)blockIdx.x + i * (int)gridDim.x;
+    return ga.reverse ? num_units - 1 - u : u;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_RING; ++i) {
@@ -254,7 +265,7 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       uint32_t a_par = 0;
       int prev_rt = -1;
       for (int u = u_begin; u < u_end; ++u) {
-        const int ue = ga.reverse ? num_units - 1 - u : u;
+        const int ue = unit_at(u);
         const int rt = ue / groups, ng = ue % groups;   // rt counts (split, row tile) pairs
         const size_t a_row = (size_t)(rt % ga.row_tiles) * ga.kb_stride + (size_t)(rt / ga.row_tiles) * ga.kb;
         const size_t kb_split = (size_t)(rt / ga.row_tiles) * ga.kb;
@@ -303,10 +314,10 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       int prev_rt = -1;
       int q = 0;  // 128-col tile sequence number (multiple of TU at unit start)
       for (int u = u_begin; u < u_end; ++u) {
-        const int rt = (ga.reverse ? num_units - 1 - u : u) / groups;
+        const int rt = unit_at(u) / groups;
         const bool new_rt = RES && (rt != prev_rt);
         const bool last_of_rt =
-            RES && (u + 1 == u_end || (ga.reverse ? num_units - 2 - u : u + 1) / groups != rt);
+            RES && (u + 1 == u_end || unit_at(u + 1) / groups != rt);
         for (int kb = 0; kb < ga.kb; ++kb) {
           uint32_t a_tile;
           int a_stage = -1;
@@ -360,8 +371,7 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
     const int n_local = (u_end - u_begin) * TU;
     float* sb = ctrl->bias_stage[eg];
     auto coords = [&](int q, int& rt, int& nt) {   // rt counts (split, row tile) pairs
-      const int u = u_begin + q / TU;
-      const int ue = ga.reverse ? num_units - 1 - u : u;
+      const int ue = unit_at(u_begin + q / TU);
       rt = ue / groups;
       nt = (ue % groups) * TU + q % TU;
     };

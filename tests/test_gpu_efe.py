@@ -175,3 +175,30 @@ def test_diffusion_elbo_loss_and_grads(precision, tol):
     w = R.update_time_importance(torch.ones(100), t, per.detach())
     assert torch.allclose(ai.time_importance_weights.cpu(), w, rtol=tol, atol=1e-6)
     assert torch.equal((t.cuda() * 99).long().clamp(0, 99).cpu(), R.time_importance_bins(t))
+
+
+def test_epistemic_estimator_matches_oracle_with_injected_draws():
+    """FunctionSpaceEpistemicEstimator.forward (core/active_inference.py:940-1063 + decoder shim) on
+    the tcgen05 GEMM path vs the oracle, with the reference's draws injected in its order."""
+    L, A, H, B, S = 32, 6, 128, 48, 3
+    ai, nets, cfg = make_ai(L, A, H)
+    est = ai.epistemic_estimator
+    own = {k: v.detach().cpu() for k, v in est.state_dict().items()
+           if not k.startswith("decoder.") and k not in ("perturbation_scale", "running_mean")}
+    est.load_state_dict(perturb_generic(own, 9, 0.05), strict=False)
+    ep = {k: v.detach().cpu().clone() for k, v in est.state_dict().items() if not k.startswith("decoder.")}
+    g = gen(77)
+    mean = torch.randn(B, L, generator=g)
+    logvar = torch.full((B, L), float(torch.log(torch.tensor(0.1))))
+    z_eps = [torch.randn(B, L, generator=g) for _ in range(S)]
+    dir_eps = [torch.randn(S * B, L, generator=g) for _ in range(4)]
+    perms = [torch.randperm(B, generator=g) for _ in range(S)]
+    with torch.no_grad():
+        want, mi, joint, marg, rm = R.epistemic_value(ep, nets["decoder"], mean, logvar, z_eps, dir_eps, perms, 0.0)
+        got, metrics = est(mean.cuda(), logvar.cuda(), S, z_noise=[e.cuda() for e in z_eps],
+                           dir_noise=[e.cuda() for e in dir_eps], perms=[p.cuda() for p in perms])
+    assert abs(metrics["epistemic/joint_term"] - float(joint)) < 1e-3 * (1 + abs(float(joint)))
+    assert abs(metrics["epistemic/marginal_term"] - float(marg)) < 1e-3 * (1 + abs(float(marg)))
+    assert abs(metrics["epistemic/mi_estimate"] - float(mi)) < 2e-3
+    assert torch.allclose(got.cpu(), want, atol=2e-3)
+    assert abs(metrics["epistemic/running_mean"] - rm) < 1e-3 * (1 + abs(rm))
