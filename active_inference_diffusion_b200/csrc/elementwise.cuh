@@ -78,8 +78,10 @@ __global__ void k_pack_bias(const float* __restrict__ src, int n, float* __restr
   if (i >= n_pad) return;
   float v = 0.f;
   if (mode == MAP_MODLN) {
+    // scale rows (j < 64) carry 1 + bias so the epilogue needs no separate "1 + scale" add; padded
+    // hidden columns get scale' = 0 and shift = 0 (their weight rows are zero too) -> output 0
     int t = i >> 7, j = i & 127;
-    if (t * 64 + (j & 63) < H) v = src[map_row(i, mode, H)];
+    if (t * 64 + (j & 63) < H) v = src[map_row(i, mode, H)] + (j < 64 ? 1.0f : 0.0f);
   } else if (i < n && src) {
     v = src[i];
   }

@@ -43,6 +43,29 @@ __device__ __forceinline__ void group_bar(int bar_id) {
   asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 }
 
+// Packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE-rn fp32 results per issue slot).
+// The epilogues are bound by the FP32 pipe's issue rate, so the hot math works on register pairs.
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  const float2 r = __fadd2_rn(make_float2(a0, a1), make_float2(b0, b1));
+  a0 = r.x; a1 = r.y;
+}
+__device__ __forceinline__ void act_gelu2(float& a, float& b) {   // act_gelu on two elements
+#ifdef AID_EXACT_GELU
+  a = act_gelu(a); b = act_gelu(b);
+#else
+  const float2 x = make_float2(a, b);
+  const float2 p = __ffma2_rn(__fmul2_rn(x, x), make_float2(0.0356774081f, 0.0356774081f),
+                              make_float2(0.7978845608f, 0.7978845608f));
+  const float2 u = __fmul2_rn(x, p);
+  float t0, t1;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  const float2 r = __ffma2_rn(hx, make_float2(t0, t1), hx);
+  a = r.x; b = r.y;
+#endif
+}
+
 template <int ACT>
 __device__ __forceinline__ void act_apply32_ct(float (&y)[32]) {
   if constexpr (ACT == ACT_SILU) {
@@ -53,7 +76,7 @@ __device__ __forceinline__ void act_apply32_ct(float (&y)[32]) {
     for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
   } else if constexpr (ACT == ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) y[j] = act_gelu(y[j]);
+    for (int j = 0; j < 32; j += 2) act_gelu2(y[j], y[j + 1]);
   }
 }
 
@@ -120,7 +143,8 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
         bias32_from_smem(sb, c * 32, y);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
+        for (int j = 0; j < 32; j += 2)
+          add2(y[j], y[j + 1], __uint_as_float(raw[j]), __uint_as_float(raw[j + 1]));
         if (c + 1 < 4) tmem_ld32(tmem_tile + (c + 1) * 32, raw);   // in flight during this chunk's math
         if (!(e.debug & 64)) act_apply32_ct<ACT>(y);
         if (n0 + 32 > e.n_valid) {
@@ -148,12 +172,12 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
         bias32_from_smem(sb, c * 32, y);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
+        for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);   // scalar: packed pairs spill here
         if (c + 1 < 4) tmem_ld32(tmem_tile + (c + 1) * 32, raw);   // in flight during this chunk's math
         if (e.resid_tiled && !(e.debug & 128)) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            float4 hv = st.res[hb][q];
+            const float4 hv = st.res[hb][q];
             y[q * 4 + 0] += hv.x; y[q * 4 + 1] += hv.y; y[q * 4 + 2] += hv.z; y[q * 4 + 3] += hv.w;
           }
           // refill this buffer: chunk c+2 of this tile, or chunk c-2 of the group's next tile
@@ -197,8 +221,21 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
           }
         }
         if (e.stats_out) {
-          int nv = min(32, max(0, e.n_valid - n0));
-          if (nv > 0) {
+          const int nv = min(32, max(0, e.n_valid - n0));
+          if (nv == 32) {                       // full chunk (every hot layer): no per-element masks
+            float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) s2 = __fadd2_rn(s2, make_float2(y[j], y[j + 1]));
+            const float m = (s2.x + s2.y) * (1.0f / 32.0f);
+            const float2 nm = make_float2(-m, -m);
+            float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float2 d = __fadd2_rn(make_float2(y[j], y[j + 1]), nm);
+              q2 = __ffma2_rn(d, d, q2);
+            }
+            stats_merge(sn, smean, sm2, 32.f, m, q2.x + q2.y);
+          } else if (nv > 0) {
             float s = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) s += (j < nv) ? y[j] : 0.f;
@@ -216,39 +253,39 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
     }
     if (e.stats_out) e.stats_out[((size_t)rt * n_tiles + nt) * TILE_M + r] = make_float2(smean, sm2);
   } else if constexpr (EPI == EPI_MODLN) {
-    const float mean = st.mean, rstd = st.rstd;
+    // y = LN(h) * (1 + scale) + shift with hn = h*rstd - mean*rstd; the packed bias of the scale
+    // rows already holds 1 + b (k_pack_bias), so one output costs 2 FADD + 2 FFMA.
+    const float rstd = st.rstd, nmr = -st.mean * st.rstd;
     __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + nt) * TILE_ELEMS;
     uint32_t rs[16], rh[16];
     tmem_ld16(tmem_tile, rs);                     // scale cols
     tmem_ld16(tmem_tile + 64, rh);                // shift cols
 #pragma unroll
     for (int c = 0; c < 4; ++c) {                 // 16 hidden columns per iteration
-      const float4* bsp = reinterpret_cast<const float4*>(sb + c * 16);        // scale biases
+      const float4* bsp = reinterpret_cast<const float4*>(sb + c * 16);        // 1 + scale biases
       const float4* bhp = reinterpret_cast<const float4*>(sb + 64 + c * 16);   // shift biases
-      const int hc0 = nt * 64 + c * 16;           // hidden column of y[0]
-      float y[16], sc[16], sh[16];
+      float y[16];
       tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { sc[j] = __uint_as_float(rs[j]); sh[j] = __uint_as_float(rh[j]); }
-      if (c + 1 < 4) {                            // next chunk's accumulators in flight during the math
-        tmem_ld16(tmem_tile + (c + 1) * 16, rs);
-        tmem_ld16(tmem_tile + 64 + (c + 1) * 16, rh);
-      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 hv = st.h[c * 4 + q];
         const float4 b1 = bsp[q], b2 = bhp[q];
-        const float hx[4] = {hv.x, hv.y, hv.z, hv.w};
-        const float bs[4] = {b1.x, b1.y, b1.z, b1.w};
-        const float bh[4] = {b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int j = q * 4 + i;
-          const float scale = sc[j] + bs[i];
-          const float shift = sh[j] + bh[i];
-          const float xn = (hx[i] - mean) * rstd;
-          y[j] = (hc0 + j < e.h_dim) ? fmaf(xn, 1.0f + scale, shift) : 0.f;
+        for (int i = 0; i < 2; ++i) {             // two hidden columns per packed instruction
+          const int j = q * 4 + i * 2;
+          const float2 hx = i ? make_float2(hv.z, hv.w) : make_float2(hv.x, hv.y);
+          const float2 bs = i ? make_float2(b1.z, b1.w) : make_float2(b1.x, b1.y);
+          const float2 bh = i ? make_float2(b2.z, b2.w) : make_float2(b2.x, b2.y);
+          const float2 scale1 = __fadd2_rn(make_float2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), bs);
+          const float2 shift = __fadd2_rn(make_float2(__uint_as_float(rh[j]), __uint_as_float(rh[j + 1])), bh);
+          const float2 hn = __ffma2_rn(hx, make_float2(rstd, rstd), make_float2(nmr, nmr));
+          const float2 o = __ffma2_rn(hn, scale1, shift);
+          y[j] = o.x; y[j + 1] = o.y;
         }
+      }
+      if (c + 1 < 4) {                            // rs/rh are consumed: next chunk's accumulators
+        tmem_ld16(tmem_tile + (c + 1) * 16, rs);
+        tmem_ld16(tmem_tile + 64 + (c + 1) * 16, rh);
       }
       if (has_next && !(e.debug & 128)) {         // refill the consumed registers for the next tile
 #pragma unroll

@@ -306,7 +306,11 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop (uniform control flow, descriptors in uniform registers); one
+    // elected lane issues the tcgen05 instructions.  With the loop under `if (lane == 0)` every MMA
+    // paid ELECT + 5 R2UR moves and the single issue thread, not the tensor pipe, set the pace
+    // (MMA-only kernels at 58 % of the pipe rate).
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N * NW);
       int stage = 0;
       uint32_t phase = 0;
@@ -343,20 +347,31 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
             tc_fence_after();
             const uint32_t b_tile = ring_smem + stage * SLOT_BYTES;
             const uint32_t d = tmem_base + (uint32_t)(((q + g * NW) & 3) * TILE_N);
+            const uint64_t ad = umma_desc_kmajor(a_tile, TILE_M * 16);
+            const uint64_t bd = umma_desc_kmajor(b_tile, NW * TILE_M * 16);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < TILE_K / 16; ++k) {
-              umma_bf16(d, umma_desc_kmajor(a_tile + k * (2 * TILE_M * 16), TILE_M * 16),
-                        umma_desc_kmajor(b_tile + k * (2 * NW * TILE_M * 16), NW * TILE_M * 16), idesc,
-                        (kb | k) ? 1u : 0u);
+              for (int k = 0; k < TILE_K / 16; ++k) {
+                // advancing the 14-bit start-address field by a constant stays inside the field
+                umma_bf16(d, ad + (uint64_t)(k * (2 * TILE_M * 16) >> 4),
+                          bd + (uint64_t)(k * (2 * NW * TILE_M * 16) >> 4), idesc, (kb | k) ? 1u : 0u);
+              }
+              umma_commit(smem_u32(&ctrl->ring_empty[stage]));
             }
-            umma_commit(smem_u32(&ctrl->ring_empty[stage]));
+            __syncwarp();
             if (++stage == ring_stages) { stage = 0; phase ^= 1; }
           }
-          if (!RES) umma_commit(smem_u32(&ctrl->ring_empty[a_stage]));
-          if (last_of_rt) umma_commit(smem_u32(&ctrl->a_empty[kb]));
+          if (elect_one()) {
+            if (!RES) umma_commit(smem_u32(&ctrl->ring_empty[a_stage]));
+            if (last_of_rt) umma_commit(smem_u32(&ctrl->a_empty[kb]));
+          }
+          __syncwarp();
         }
+        if (elect_one()) {
 #pragma unroll
-        for (int t = 0; t < TU; ++t) umma_commit(smem_u32(&ctrl->acc_full[(q + t) & 3]));
+          for (int t = 0; t < TU; ++t) umma_commit(smem_u32(&ctrl->acc_full[(q + t) & 3]));
+        }
+        __syncwarp();
         q += TU;
         if (new_rt) { a_par ^= 1; prev_rt = rt; }
       }
