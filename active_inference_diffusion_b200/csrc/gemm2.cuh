@@ -13,10 +13,10 @@
 //   B  : 128 x 64 half tiles (n-tile 2*ng + c of the 256-column unit) in a ring of stages.
 //   D  : TMEM accumulators of its own 128 rows x 256 columns, two units in flight.
 // Protocol (all mbarriers in each CTA's control block at identical offsets):
-//   ring_full[s]  local   : the CTA's own bulk copies (complete_tx).
-//   peer_full[s]  leader  : rank 1's "forwarder" thread waits on its local a_full/ring_full and
-//                           arrives remotely here, so the leader's single MMA thread knows both
-//                           halves (and rank 1's A k-block) are in shared memory.
+//   ring_full[s]          : the CTA's own bulk copies (complete_tx); the LEADER's copy additionally
+//                           takes a remote arrive from rank 1's "forwarder" thread (which waits on
+//                           rank 1's a_full/ring_full), so one wait tells the leader's MMA warp that
+//                           both halves (and rank 1's A k-block) are in shared memory.
 //   ring_empty[s], a_empty[kb], acc_full[slot] : signalled in BOTH CTAs by the leader's
 //                           tcgen05.commit ... multicast::cluster (mask 0b11).
 //   acc_empty[slot] leader : 8 arrivals = 4 epilogue warps of each CTA (rank 1 arrives remotely).
@@ -118,7 +118,8 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_RING2; ++i) {
-      mbar_init(smem_u32(&ctrl->ring_full[i]), 1);
+      // leader: own producer's expect_tx arrive + rank 1's forwarder (one wait per stage for the MMA warp)
+      mbar_init(smem_u32(&ctrl->ring_full[i]), rank == 0 ? 2 : 1);
       mbar_init(smem_u32(&ctrl->ring_empty[i]), 1);
       mbar_init(smem_u32(&ctrl->peer_full[i]), 1);
     }
@@ -198,13 +199,13 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
         for (int kb = 0; kb < ga.kb; ++kb) {
           if (RES && new_rp) mbar_wait(smem_u32(&ctrl->a_full[kb]), a_par, ga.err, 9);
           mbar_wait(smem_u32(&ctrl->ring_full[stage]), phase, ga.err, 10);
-          mbar_arrive_cluster(smem_u32(&ctrl->peer_full[stage]), 0);
+          mbar_arrive_cluster(smem_u32(&ctrl->ring_full[stage]), 0);
           if (++stage == ring_stages) { stage = 0; phase ^= 1; }
         }
         if (new_rp) { a_par ^= 1; prev_rp = rp; }
       }
-    } else if (lane == 0) {
-      // ===================== MMA issuer (leader) =====================
+    } else if (rank == 0) {
+      // ===================== MMA issuer (leader): whole warp, one elected lane issues ==========
       constexpr uint32_t idesc = umma_idesc_bf16(2 * TILE_M, 2 * TILE_N);
       int stage = 0;
       uint32_t phase = 0, a_par = 0;
@@ -229,24 +230,30 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
         const uint32_t d = tmem_base + (uint32_t)((q & 3) * TILE_N);
         for (int kb = 0; kb < ga.kb; ++kb) {
           if (RES && new_rp) mbar_wait(smem_u32(&ctrl->a_full[kb]), a_par, ga.err, 5);
-          mbar_wait(smem_u32(&ctrl->ring_full[stage]), phase, ga.err, 7);
-          if (!(ga.debug & 256)) mbar_wait(smem_u32(&ctrl->peer_full[stage]), phase, ga.err, 11);
+          mbar_wait(smem_u32(&ctrl->ring_full[stage]), phase, ga.err, 7);   // both halves are in
           tc_fence_after();
           const uint32_t s_base = ring_smem + stage * STAGE_BYTES2;
           const uint32_t a_tile = RES ? a_smem + kb * TILE_BYTES : s_base;
           const uint32_t b_tile = RES ? s_base : s_base + TILE_BYTES;
+          const uint64_t ad = umma_desc_kmajor(a_tile, TILE_M * 16);
+          const uint64_t bd = umma_desc_kmajor(b_tile, TILE_M * 16);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TILE_K / 16; ++k) {
-            umma2_bf16(d, umma_desc_kmajor(a_tile + k * (2 * TILE_M * 16), TILE_M * 16),
-                       umma_desc_kmajor(b_tile + k * (2 * TILE_M * 16), TILE_M * 16), idesc,
-                       (kb | k) ? 1u : 0u);
+            for (int k = 0; k < TILE_K / 16; ++k) {
+              umma2_bf16(d, ad + (uint64_t)(k * (2 * TILE_M * 16) >> 4), bd + (uint64_t)(k * (2 * TILE_M * 16) >> 4),
+                         idesc, (kb | k) ? 1u : 0u);
+            }
+            umma2_commit_both(smem_u32(&ctrl->ring_empty[stage]));
+            if (last_of_rp) umma2_commit_both(smem_u32(&ctrl->a_empty[kb]));
           }
-          umma2_commit_both(smem_u32(&ctrl->ring_empty[stage]));
-          if (last_of_rp) umma2_commit_both(smem_u32(&ctrl->a_empty[kb]));
+          __syncwarp();
           if (++stage == ring_stages) { stage = 0; phase ^= 1; }
         }
+        if (elect_one()) {
 #pragma unroll
-        for (int t = 0; t < TU; ++t) umma2_commit_both(smem_u32(&ctrl->acc_full[(q + t) & 3]));
+          for (int t = 0; t < TU; ++t) umma2_commit_both(smem_u32(&ctrl->acc_full[(q + t) & 3]));
+        }
+        __syncwarp();
         q += TU;
         if (new_rp) { a_par ^= 1; prev_rp = rp; }
       }
