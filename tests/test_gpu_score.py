@@ -80,6 +80,8 @@ def test_score_clamp_saturation():
     (64, 17, 128, 2, 10, "linear"),
     (32, 17, 128, 2, 25, "cosine"),
     (128, 17, 512, 6, 50, "cosine"),
+    (128, 376, 512, 6, 4, "cosine"),     # Humanoid-v4 observation width (BASELINE configs[3])
+    (128, 128, 512, 6, 4, "cosine"),     # obs = latent (how DiffusionActiveInference builds it)
 ])
 @pytest.mark.parametrize("B", [7, 256])
 def test_reverse_diffusion(L, O, H, NB, T, sched, B):
@@ -132,3 +134,27 @@ def test_collector_sampler():
         want = R.collector_sample(params, R.make_schedule(T), z0, obs, list(noise), max_steps)
         got = diff.collector_sample(net, obs.cuda(), max_steps, z_init=z0.cuda(), noise=noise.cuda())
     assert rel_l2(got, want) < LATENT_TOL, rel_l2(got, want)
+
+
+def test_full_size_rows_are_independent_and_shardable():
+    """BASELINE configs[1] size (65,536 candidates): every row depends only on its own inputs, so
+    a row's latent inside the full batch must equal, BIT FOR BIT, the latent of the same row sampled
+    in a 200-row slice with the same noise -- the property that makes row sharding over GPUs exact
+    (no data-path collective) -- and the full-size output must be finite and non-degenerate."""
+    from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess
+    L, O, H, NB, T, B = 128, 17, 512, 6, 3, 65536
+    net, _ = make_score_net(L, O, H, NB, device="cuda")
+    diff = LatentDiffusionProcess(DiffusionConfig(num_diffusion_steps=T), L).cuda()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    obs = torch.randn(B, O, device="cuda", generator=g)
+    zT = torch.randn(B, L, device="cuda", generator=g)
+    noise = torch.randn(T - 1, B, L, device="cuda", generator=g)
+    with torch.no_grad():
+        full = diff.generate_latent_trajectory(net, B, obs, z_init=zT, noise=noise, return_trajectory=False)[-1]
+        for lo in (0, 31337, B - 200):
+            sl = slice(lo, lo + 200)
+            part = diff.generate_latent_trajectory(net, 200, obs[sl], z_init=zT[sl], noise=noise[:, sl].contiguous(),
+                                                   return_trajectory=False)[-1]
+            assert torch.equal(part, full[sl]), lo
+    assert torch.isfinite(full).all()
+    assert float(full.std()) > 1e-3
