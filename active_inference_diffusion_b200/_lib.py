@@ -112,6 +112,11 @@ def _declare_train(l: ctypes.CDLL) -> None:
                               c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p]
 
 
+def _declare_misc(l: ctypes.CDLL) -> None:
+    l.aid_time_importance_update.restype = c_int32
+    l.aid_time_importance_update.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]
+
+
 def lib() -> ctypes.CDLL:
     """Load the CUDA extension; fail loudly when it has not been built."""
     global _lib
@@ -123,6 +128,7 @@ def lib() -> ctypes.CDLL:
         l = ctypes.CDLL(LIB_PATH)
         _declare(l)
         _declare_train(l)
+        _declare_misc(l)
         _lib = l
     return _lib
 
@@ -221,6 +227,19 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = Non
     check(l.aid_gemm_nt(ptr(a), a.stride(0), a.stride(1), ptr(b), b.stride(0), b.stride(1), ptr(bias), ptr(out),
                         M, N, K, prec, ptr(ws), ws_bytes, stream_ptr(dev)), "aid_gemm_nt")
     return out
+
+
+def time_importance_update(t: torch.Tensor, loss: torch.Tensor, weights: torch.Tensor,
+                           want_bins: bool = False) -> Optional[torch.Tensor]:
+    """In-place sequential EMA of `weights` [n_bins] over the batch (aid_time_importance_update)."""
+    dev = require_cuda(t, loss, weights)
+    t, loss = f32c(t.detach().reshape(-1)), f32c(loss.detach().reshape(-1))
+    if weights.dtype != torch.float32 or not weights.is_contiguous():
+        raise ValueError("weights must be a contiguous float32 tensor")
+    bins = torch.empty(t.numel(), dtype=torch.int64, device=dev) if want_bins else None
+    check(lib().aid_time_importance_update(ptr(t), ptr(loss), t.numel(), ptr(weights), weights.numel(), ptr(bins),
+                                           stream_ptr(dev)), "aid_time_importance_update")
+    return bins
 
 
 def profile_select(epi: int, k: int = 0, n: int = 0) -> None:

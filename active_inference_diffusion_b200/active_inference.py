@@ -28,7 +28,7 @@ from .diffusion import LatentDiffusionProcess
 from .heads import (DiffusionConditionedPolicy, HeadsBundle, LatentDynamicsModel, ValueNetwork,
                     make_reward_predictor)
 from .score_network import LatentScoreNetwork
-from . import autograd_path
+from . import _lib, autograd_path
 
 
 class FunctionSpaceEpistemicEstimator(nn.Module):
@@ -384,15 +384,15 @@ class DiffusionActiveInference(nn.Module):
         return (idx.float() + torch.rand(batch_size, device=device)) / 100.0
 
     def _update_time_importance(self, t: torch.Tensor, loss: torch.Tensor) -> None:
-        """Sequential per-sample EMA over 100 bins (:750-771).  The reference does B x 3 host syncs;
-        here the batch is moved to the host once and the same python-float arithmetic is replayed."""
+        """Sequential per-sample EMA over 100 bins (:750-771).  The reference does B x 3 host syncs in
+        a Python loop; here one kernel (one thread per bin) replays the batch in order with the same
+        double arithmetic and fp32 rounding -- bit-identical, no host round trip."""
         if not hasattr(self, "time_importance_weights"):
             self.time_importance_weights = torch.ones(100, device=t.device)
-        idx = (t * 99).long().clamp(0, 99).cpu().tolist()
         if loss.dim() > 1:
             loss = loss.view(loss.shape[0], -1).sum(dim=1)
-        lv = loss.cpu()
-        w = self.time_importance_weights.cpu()
-        for i, b in enumerate(idx):
-            w[b] = 0.99 * w[b].item() + 0.01 * lv[i].item()
-        self.time_importance_weights = w.to(t.device)
+        w = self.time_importance_weights
+        if w.device != t.device or w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.to(t.device, torch.float32).contiguous()
+            self.time_importance_weights = w
+        _lib.time_importance_update(t, loss, w)

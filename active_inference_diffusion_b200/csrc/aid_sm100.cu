@@ -111,7 +111,8 @@ static void plin_shape(PLin& p, int n, int k, bool modln = false) {
   p.k = k;
   p.kb = ceil_div(k, TILE_K);
   p.n_tiles = modln ? ceil_div(n / 2, 64) : ceil_div(n, TILE_N);
-  p.nw = (!use_pairs() && p.n_tiles % 2 == 0) ? 2 : 1;
+  static const bool narrow = getenv("AID_DEBUG") && (atoi(getenv("AID_DEBUG")) & 4);   // knob: N=128 units
+  p.nw = (!use_pairs() && !narrow && p.n_tiles % 2 == 0) ? 2 : 1;
 }
 static size_t plin_w_bytes(const PLin& p) { return (size_t)p.n_tiles * p.kb * TILE_BYTES; }
 static size_t plin_b_bytes(const PLin& p) { return (size_t)p.n_tiles * TILE_N * sizeof(float); }

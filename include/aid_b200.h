@@ -202,6 +202,14 @@ int32_t aid_fp_belief_update(const double* mean, const double* variance, const d
                              double noise_scale, double min_variance, double max_variance,
                              double* mean_out, double* variance_out, double* precision_out, void* stream);
 
+/* ---- _update_time_importance — core/active_inference.py:750-771 -----------------------------
+ * weights[bin(t_i)] <- 0.99*w + 0.01*loss_i for i = 0..n-1 in batch order (double arithmetic, fp32
+ * storage after every step, exactly as the reference's .item() loop), bin(t) =
+ * clamp((int64)(t*99), 0, n_bins-1).  weights [n_bins] fp32 updated in place; bins_out (optional)
+ * [n] int64 receives the bin indices. */
+int32_t aid_time_importance_update(const float* t, const float* loss, int32_t n, float* weights,
+                                   int32_t n_bins, int64_t* bins_out, void* stream);
+
 /* ---- primitive exposed for tests: y = act(x W^T + b) through the tcgen05 path --------------
  * x [M,K], w [N,K], bias [N] or NULL, y [M,N]; act: 0 none, 1 SiLU, 2 ReLU, 3 GELU(erf).
  * via_packed != 0 routes the result through the bf16 packed epilogue and back (tests EPI_PACK). */

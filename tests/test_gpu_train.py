@@ -90,3 +90,23 @@ def test_pair_kernel_variant_subprocess():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n", [1, 37, 4096])
+def test_time_importance_update_is_bit_exact(n):
+    """core/active_inference.py:750-771 on the device: same sequential double arithmetic with fp32
+    storage as the reference's .item() loop -> identical bits; bin indices exact (integer work)."""
+    from active_inference_diffusion_b200 import _lib
+    from oracle import restatement as R
+    g = gen(n)
+    t = torch.rand(n, generator=g)
+    t[0] = 0.0
+    if n > 2:
+        t[1], t[2] = 0.999999, 1.0          # top bin / clamp
+    loss = torch.randn(n, generator=g).abs() * 3
+    w0 = torch.rand(100, generator=g) + 0.5
+    want = R.update_time_importance(w0, t, loss)
+    w = w0.clone().cuda()
+    bins = _lib.time_importance_update(t.cuda(), loss.cuda(), w, want_bins=True)
+    assert torch.equal(w.cpu(), want)
+    assert torch.equal(bins.cpu(), R.time_importance_bins(t))
