@@ -200,12 +200,16 @@ class DiffusionActiveInference(nn.Module):
         return autograd_path.linear(autograd_path.seq(m[2], h2), m[3].weight, m[3].bias)
 
     def predict_reward_from_latent(self, latent: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        out = self._heads.head_forward(3, latent.to(self.device))
+        latent = latent.to(self.device)
+        if autograd_path.needs_graph(self.reward_predictor, latent):
+            out = autograd_path.seq(self.reward_predictor, latent)
+        else:
+            out = self._heads.head_forward(3, latent)
         return out[:, 0], torch.exp(torch.clamp(out[:, 1], min=-5, max=2))
 
     def predict_next_latent(self, latent: torch.Tensor, action: torch.Tensor):
         latent, action = latent.to(self.device), action.to(self.device)
-        next_mean = latent + self.latent_dynamics(latent, action)      # 2z + f(z,a), SURVEY fact 10
+        next_mean = latent + self.latent_dynamics(latent, action)      # 2z + f(z,a), SURVEY fact 10 (differentiable when recording)
         return next_mean, torch.full_like(next_mean, float(np.log(0.1)))
 
     def reparameterize(self, mean: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
@@ -263,8 +267,15 @@ class DiffusionActiveInference(nn.Module):
         if epistemic is None and self.use_epistemic:
             epistemic, metrics = self._epistemic_sequence(latent, h, K, policy_noise, reparam_noise,
                                                           num_ambiguity_samples)
-        efe, first_action, prag, cons = self._heads.efe_rollout(
-            latent, h, K, cfg, self.preference_temperature, policy_noise, reparam_noise, epistemic)
+        if any(autograd_path.needs_graph(m, latent) for m in (self.policy_network, self.latent_dynamics,
+                                                               self.value_network, self.reward_predictor)):
+            # a graph is being recorded (policy training, agents/state_agent.py:165-177): differentiable
+            # evaluation of the same rollout, every Linear on aid_gemm_nt
+            efe, first_action, prag, cons = autograd_path.efe_rollout(
+                self, latent, h, K, policy_noise, reparam_noise, epistemic)
+        else:
+            efe, first_action, prag, cons = self._heads.efe_rollout(
+                latent, h, K, cfg, self.preference_temperature, policy_noise, reparam_noise, epistemic)
         self.last_first_action = first_action
         if epistemic is not None:
             last = epistemic.view(K, h)[:, -1]

@@ -162,6 +162,79 @@ def score_forward(net, z_t: torch.Tensor, time: torch.Tensor,
     return s * time_weight if time_weight is not None else s
 
 
+# ---------------------------------------------------------------------------------------------
+# Differentiable EFE heads / rollout: used when a caller records a graph through the heads
+# (policy / value / dynamics training, agents/state_agent.py:162-238).  Same math as the fused
+# rollout kernel (aid_efe_rollout); every Linear on aid_gemm_nt.
+
+def needs_graph(module, *tensors) -> bool:
+    """True when autograd is recording and an input or a parameter of `module` requires grad."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+def policy_forward(pol, z: torch.Tensor, eps: Optional[torch.Tensor]):
+    """models/policy_networks.py:95-146 -> (action, mean, log_std clamped, std)."""
+    h = _seq(pol.latent_encoder, z)
+    h = h + _seq(pol.trunk, h)
+    mean = _seq(pol.mean_head, h)
+    log_std = torch.clamp(_seq(pol.log_std_head, h), pol.log_std_min, pol.log_std_max)
+    std = torch.exp(log_std)
+    action = mean if eps is None else mean + std * eps
+    return action, mean, log_std, std
+
+
+def dynamics_forward(dyn, state: torch.Tensor, action: torch.Tensor) -> torch.Tensor:
+    """models/dynamics_models.py:47-67 (residual)."""
+    return state + _seq(dyn.network, torch.cat([state, action], dim=-1))
+
+
+def value_forward(val, state: torch.Tensor, time: torch.Tensor) -> torch.Tensor:
+    """models/value_networks.py:47-60 -> [B, 1]."""
+    emb = val.time_embed[0]
+    e = _sinusoid(time, val.time_embed_dim, emb.freq_scale)
+    t_emb = F.relu(linear(e, val.time_embed[1].weight, val.time_embed[1].bias))
+    return _seq(val.network, torch.cat([state, t_emb], dim=-1))
+
+
+def efe_rollout(ai, latent: torch.Tensor, horizon: int, num_trajectories: int, policy_noise: torch.Tensor,
+                reparam_noise: torch.Tensor, epistemic: Optional[torch.Tensor]):
+    """compute_expected_free_energy_diffusion (core/active_inference.py:314-396) as a differentiable
+    graph.  Returns (efe [B], first_action [B,A], pragmatic_last [K,B], consistency_last [K,B])."""
+    cfg = ai.config
+    ew, pw, cw, gamma = (float(cfg.epistemic_weight), float(cfg.pragmatic_weight),
+                         float(cfg.consistency_weight), float(cfg.discount_factor))
+    B = latent.shape[0]
+    std_next = math.exp(0.5 * math.log(0.1))
+    total = torch.zeros(B, device=latent.device)
+    first_action, prag_l, cons_l = None, [], []
+    for k in range(num_trajectories):
+        cur, traj = latent, torch.zeros(B, device=latent.device)
+        for t in range(horizon):
+            d = k * horizon + t
+            action, _, _, std = policy_forward(ai.policy_network, cur, policy_noise[d])
+            if d == 0:
+                first_action = action
+            mean = cur + dynamics_forward(ai.latent_dynamics, cur, action)       # 2z + f(z,a), SURVEY fact 10
+            nxt = mean + reparam_noise[d] * std_next
+            r = _seq(ai.reward_predictor, nxt)[:, 0]
+            prag = pw * (r / ai.preference_temperature)
+            prag = prag + value_forward(ai.value_network, nxt, torch.full((B,), float(t), device=latent.device)).squeeze(-1)
+            cons = -(0.5 + 0.5 * math.log(2 * math.pi) + torch.log(std)).sum(-1)
+            step = pw * prag + cw * cons
+            if epistemic is not None:
+                step = step + ew * epistemic[d]
+            traj = traj + (gamma ** t) * step
+            cur = nxt
+        total = total + traj / num_trajectories
+        prag_l.append(prag)
+        cons_l.append(cons)
+    return total, first_action, torch.stack(prag_l), torch.stack(cons_l)
+
+
 class EMALogMeanExp(torch.autograd.Function):
     """log(mean(exp(x))) with the MINE running-mean gradient (core/active_inference.py:815-826)."""
 

@@ -75,9 +75,13 @@ class DiffusionConditionedPolicy(nn.Module):
 
     def forward(self, z: torch.Tensor, deterministic: bool = False
                 ) -> Tuple[torch.Tensor, torch.Tensor, dist.Distribution]:
-        out = _bundle_of(self).head_forward(0, z)
+        from . import autograd_path
         A = self.action_dim
-        mean, log_std = out[:, :A], out[:, A:]
+        if autograd_path.needs_graph(self, z):      # training: differentiable evaluation, GEMMs on aid_gemm_nt
+            _, mean, log_std, _ = autograd_path.policy_forward(self, z, None)
+        else:
+            out = _bundle_of(self).head_forward(0, z)
+            mean, log_std = out[:, :A], out[:, A:]
         log_std = torch.clamp(log_std, self.log_std_min, self.log_std_max)
         distribution = dist.Normal(mean, torch.exp(log_std))
         action = mean if deterministic else distribution.rsample()
@@ -110,6 +114,9 @@ class ValueNetwork(nn.Module):
         self._owner = None
 
     def forward(self, state: torch.Tensor, time: torch.Tensor) -> torch.Tensor:
+        from . import autograd_path
+        if autograd_path.needs_graph(self, state):
+            return autograd_path.value_forward(self, state, time)
         return _bundle_of(self).head_forward(2, state, time)
 
 
@@ -128,6 +135,9 @@ class LatentDynamicsModel(nn.Module):
         self._owner = None
 
     def forward(self, state: torch.Tensor, action: torch.Tensor) -> torch.Tensor:
+        from . import autograd_path
+        if autograd_path.needs_graph(self, state, action):
+            return autograd_path.dynamics_forward(self, state, action)
         return _bundle_of(self).head_forward(1, state, action)
 
 

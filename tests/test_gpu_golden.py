@@ -43,8 +43,9 @@ def test_efe_vs_reference_golden():
     ai = ai.to("cuda")
     ai.use_epistemic = False
     e = fx["efe_zero"]
-    got, info = ai.compute_expected_free_energy_diffusion(fx["z"].cuda(), horizon=e["h"], num_trajectories=e["K"],
-                                                          policy_noise=e["policy_noise"].cuda(),
-                                                          reparam_noise=e["reparam_noise"].cuda())
+    with torch.no_grad():        # the fused rollout kernel (a recorded graph takes the differentiable path)
+        got, info = ai.compute_expected_free_energy_diffusion(fx["z"].cuda(), horizon=e["h"], num_trajectories=e["K"],
+                                                              policy_noise=e["policy_noise"].cuda(),
+                                                              reparam_noise=e["reparam_noise"].cuda())
     assert rel_l2(got, e["efe"]) < 2e-2, rel_l2(got, e["efe"])
     assert int(torch.argmin(got)) == int(torch.argmin(e["efe"]))
