@@ -350,6 +350,7 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
             const uint64_t ad = umma_desc_kmajor(a_tile, TILE_M * 16);
             const uint64_t bd = umma_desc_kmajor(b_tile, NW * TILE_M * 16);
             if (elect_one()) {
+              if (!(ga.debug & 1024))   // 1024: no MMAs (accumulators keep their content): epilogue-only timing
 #pragma unroll
               for (int k = 0; k < TILE_K / 16; ++k) {
                 // advancing the 14-bit start-address field by a constant stays inside the field
