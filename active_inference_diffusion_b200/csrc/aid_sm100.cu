@@ -192,7 +192,22 @@ static int launch_gemm_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t 
   const bool prof = g_prof.on && g_prof.epi == EPI && g_prof.kb == ga.kb && g_prof.n_tiles == ga.n_tiles &&
                     g_prof.used < 200000;
   if (prof) cudaEventRecord(prof_event(), st);
-  kern<<<grid, GEMM_THREADS, smem, st>>>(ga, ea, ring);
+  {
+    // programmatic stream serialization: this grid may begin (prologue only, see pdl_wait in the
+    // kernel) while the previous kernel of the stream drains
+    static const bool pdl = !(getenv("AID_DEBUG") && (atoi(getenv("AID_DEBUG")) & 2048));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && !prof) ? 1 : 0;
+    AID_CHECK(cudaLaunchKernelEx(&cfg, kern, ga, ea, ring));
+  }
   if (prof) cudaEventRecord(prof_event(), st);
   AID_LAUNCH_CHECK("gemm_kernel");
   return 0;

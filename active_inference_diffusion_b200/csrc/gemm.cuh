@@ -248,10 +248,14 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
     tmem_alloc(smem_u32(&ctrl->tmem_base), 512);
     tmem_relinquish();
   }
+  // Programmatic dependent launch: the prologue above (barrier init, TMEM allocation) overlaps the
+  // tail of the previous kernel of the chain; nothing below touches global memory before the wait.
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== producer =====================
