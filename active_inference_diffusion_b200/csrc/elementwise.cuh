@@ -17,6 +17,18 @@ __device__ __forceinline__ void chunk_coords(size_t idx, int kb_total, int& rt, 
   rt = (int)(tile / kb_total);
 }
 
+// Same work item, but neighbouring threads take neighbouring 16-byte chunks of ONE row: the mapping
+// for kernels that read row-major fp32 (8 lanes cover 256 contiguous bytes of a row; the packed
+// stores then form 64-byte runs).
+__device__ __forceinline__ void chunk_coords_rowmajor(size_t idx, int kb_total, int& rt, int& kb, int& r,
+                                                      int& ch) {
+  ch = (int)(idx & 7);
+  r = (int)((idx >> 3) & 127);
+  size_t tile = idx >> 10;
+  kb = (int)(tile % kb_total);
+  rt = (int)(tile / kb_total);
+}
+
 // nw: packed tiles are nw*128 rows tall (weights of N=256 MMAs: nw = 2); rt counts 128-row tiles.
 __device__ __forceinline__ void store_chunk(__nv_bfloat16* dst, int rt, int kb, int kb_total, int r,
                                             int ch, const float (&v)[8], int nw = 1) {
@@ -51,7 +63,7 @@ __global__ void k_pack_rows(const float* __restrict__ src, int rows, int cols, i
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     int rt, kb, r, ch;
-    chunk_coords(idx, kb_total, rt, kb, r, ch);
+    chunk_coords_rowmajor(idx, kb_total, rt, kb, r, ch);
     int prow = rt * TILE_M + r;
     int c0 = kb * TILE_K + ch * 8;
     float v[8];
@@ -273,8 +285,8 @@ __global__ void k_ln_act(const LnArgs a) {
     stats_merge(sn, mean, m2, (float)min(TILE_N, a.n - p * TILE_N), s.x, s.y);
   }
   const float rstd = rsqrtf(m2 / (float)a.n + 1e-5f);
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {   // unrolled: all 16 float4 loads of the 64 columns in flight
     float y[32];
     const int c0 = kb * 64 + half * 32;
 #pragma unroll
