@@ -1,5 +1,5 @@
 """tcgen05 GEMM primitive vs torch on bf16-rounded operands (products exact in fp32, so only the
-accumulation order differs): validates the swizzled tile layout, UMMA descriptors, TMEM
+accumulation order differs): validates the packed (K-major, no-swizzle) tile layout, UMMA descriptors, TMEM
 epilogue addressing, ring/accumulator pipelines and every tiling mode."""
 import pytest
 import torch
@@ -16,9 +16,9 @@ SHAPES = [
     (200, 96, 100),      # ragged M, N, K
     (1, 8, 3),           # degenerate
     (1000, 512, 512),    # resident A, 4 n-tiles, 8 row tiles
-    (300, 512, 2048),    # streamed A, G=4
-    (257, 256, 1024),    # streamed A, G=2
-    (129, 128, 640),     # streamed A, G=1
+    (300, 512, 2048),    # streamed A, two 256-column units per row tile
+    (257, 256, 1024),    # streamed A, one unit per row tile
+    (129, 128, 640),     # streamed A, N=128 MMAs (odd n-tile count)
     (3000, 2048, 512),   # many units per CTA
     (40000, 1024, 512),  # > 148 row tiles: persistent loop over several row tiles per CTA
 ]
