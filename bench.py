@@ -280,7 +280,7 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); burst figure {peaks['burst']}",
                 "launches_timed": k_n, "avg_launch_ms": per_launch_ms, "flops_per_launch": fc1_flops,
-                "traffic": 296.9e6, "traffic_note": "dram bytes read+written per launch (86.0 + 210.9 MB) from profiles/r1_ncu_full_gemm_kernels_v2.csv; algorithmic: 67 MB packed A in + 268 MB packed activations out",
+                "traffic": 295.1e6, "traffic_note": "dram bytes read+written per launch (86.0 + 209.1 MB) from profiles/r1_ncu_full_gemm_kernels_v3.csv; algorithmic: 67 MB packed A in + 268 MB packed activations out",
                 "whole_step_tflops": step_tflops, "whole_step_frac_of_peak": step_tflops / peak},
             "cpu_baseline": cb,
         }
