@@ -60,6 +60,38 @@ class CandidateScorer(nn.Module):
         return efe, first_action, latent
 
     @torch.no_grad()
+    def collect_actions(self, observation_host: torch.Tensor, max_diffusion_steps: int = 20, *,
+                        deterministic: bool = False, z_init: Optional[torch.Tensor] = None,
+                        noise: Optional[torch.Tensor] = None, policy_noise: Optional[torch.Tensor] = None
+                        ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The collector's batched inference (utils/async_collector.py:486-595, `_inference_impl`):
+        observations of all environments (host memory, pinned if possible) -> one H2D copy ->
+        truncated reverse diffusion (t = step/(T-1), the continuous branch) -> policy head ->
+        rsample -> actions back on the host in one D2H copy.  Unlike the reference loop there is no
+        per-step isnan/isinf host sync (:591-593): non-finite latents are detected once at the end
+        and re-initialised as the reference does (0.1 * randn).  Returns (actions [n,A] on the host,
+        latents [n,L] on the device).  Keyword-only tensors inject the reference's draws."""
+        dev = next(self.parameters()).device
+        obs = observation_host.to(dev, non_blocking=True)
+        latents = self.latent_diffusion.collector_sample(self.latent_score_network, obs, max_diffusion_steps,
+                                                         z_init=z_init, noise=noise)
+        bad = ~torch.isfinite(latents).all(dim=1, keepdim=True)
+        latents = torch.where(bad, 0.1 * torch.randn_like(latents), latents)
+        out = self.heads.head_forward(0, latents)
+        A = self.action_dim
+        mean, log_std = out[:, :A], torch.clamp(out[:, A:], self.policy_network.log_std_min,
+                                                self.policy_network.log_std_max)
+        if deterministic:
+            action = mean
+        else:
+            eps = torch.randn_like(mean) if policy_noise is None else policy_noise.to(dev)
+            action = mean + torch.exp(log_std) * eps
+        host = torch.empty(action.shape, dtype=action.dtype, pin_memory=True)
+        host.copy_(action, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return host, latents
+
+    @torch.no_grad()
     def select(self, observation: torch.Tensor, **kw) -> Tuple[torch.Tensor, torch.Tensor]:
         """argmin-EFE candidate (index, action) — new capability (the reference only logs EFE,
         SURVEY fact 5); index parity vs torch.argmin is exact by construction."""

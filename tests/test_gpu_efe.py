@@ -245,3 +245,30 @@ def test_policy_training_gradients_through_efe_rollout():
     zo = z.clone().requires_grad_(True)
     R.value_forward(nets["value"], zo, torch.zeros(B)).sum().backward()
     assert rel_l2(zz.grad, zo.grad) < 2e-3
+
+
+def test_collector_inference_path_matches_oracle():
+    """utils/async_collector.py:508-595 (`_inference_impl`): truncated reverse diffusion with
+    t = step/(T-1) + policy rsample, host observations in, host actions out."""
+    from active_inference_diffusion_b200 import ActiveInferenceConfig, CandidateScorer, DiffusionConfig
+    L, O, A, H, T, n_env, steps = 32, 17, 6, 128, 10, 11, 6
+    torch.manual_seed(5)
+    cfg = ActiveInferenceConfig(hidden_dim=H, latent_dim=L, device="cpu", diffusion=DiffusionConfig(num_diffusion_steps=T))
+    m = CandidateScorer(O, A, cfg).eval()
+    m.latent_score_network.load_state_dict(perturb_state_dict(m.latent_score_network.state_dict()))
+    m.policy_network.load_state_dict(perturb_generic(m.policy_network.state_dict(), 7, 0.05))
+    sp = {k: v.detach().clone() for k, v in m.latent_score_network.state_dict().items()}
+    pp = {k: v.detach().clone() for k, v in m.policy_network.state_dict().items()}
+    m = m.cuda()
+    g = gen(8)
+    obs = torch.randn(n_env, O, generator=g)
+    z0 = torch.randn(n_env, L, generator=g)
+    noise = torch.randn(steps - 1, n_env, L, generator=g)
+    pe = torch.randn(n_env, A, generator=g)
+    with torch.no_grad():
+        wz = R.collector_sample(sp, R.make_schedule(T), z0, obs, list(noise), steps)
+        wa, _, _, _ = R.policy_forward(pp, wz, pe)
+    act, lat = m.collect_actions(obs, steps, z_init=z0.cuda(), noise=noise.cuda(), policy_noise=pe)
+    assert not act.is_cuda and act.shape == (n_env, A)
+    assert rel_l2(lat, wz) < BF16_TOL, rel_l2(lat, wz)
+    assert rel_l2(act, wa) < BF16_TOL, rel_l2(act, wa)
