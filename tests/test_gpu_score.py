@@ -20,6 +20,8 @@ CONFIGS = [  # L, O, H, NB
     (64, 17, 128, 2),
     (32, 17, 128, 2),     # reference CLI dims (examples/train_mujoco.py:150-172): latent 32, hidden 128
     (128, 17, 512, 6),    # BASELINE config #1/#2 dims
+    (64, 40, 192, 3),     # hidden width not a multiple of 128: padded n-tiles, N=128 MMA units, ragged LN partials
+    (20, 5, 64, 1),       # smallest legal dims (latent % 4 == 0, hidden % 64 == 0)
 ]
 
 
