@@ -96,13 +96,13 @@ struct PLin {
   int nw = 1;              // packed tile height in n-tiles: 2 -> 256-row tiles for N=256 MMAs
 };
 
-// CTA-pair kernels (gemm2.cuh, tcgen05 cta_group::2) are opt-in (AID_PAIRS=1): they are correct
-// (the whole GPU suite passes with them) but measured SLOWER than the single-CTA kernels on B200
-// for this network (DESIGN.md "what was tried"): the single-CTA MMA stream already runs at the
-// power-limited tensor rate with or without weight loads, so halving weight traffic buys nothing,
-// while the leader's single issue thread pays three mbarrier waits per 512-cycle stage.
+// CTA-pair kernels (gemm2.cuh, tcgen05.mma.cta_group::2) are the default for every layer whose padded
+// width is a multiple of 256: each CTA fetches half of every weight tile and the UMMA reads 8 KiB
+// instead of 12 KiB of operands per K=16 step, which takes the shared-memory port out of the
+// critical path (MMA stream with loads: 1.83 PFLOP/s vs 1.60 for the single-CTA kernel; mlp.0
+// 145 -> 114 us).  AID_PAIRS=0 selects the single-CTA kernels (weights then packed 256 rows tall).
 static bool use_pairs() {
-  static const bool on = getenv("AID_PAIRS") && atoi(getenv("AID_PAIRS")) != 0;
+  static const bool on = !(getenv("AID_PAIRS") && atoi(getenv("AID_PAIRS")) == 0);
   return on;
 }
 

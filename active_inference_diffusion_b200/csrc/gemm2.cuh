@@ -59,6 +59,18 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(rank));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// Same, without the release fence: for the forwarder, whose signal only relays the completion of
+// TMA writes (async proxy, already complete when its local barrier flipped) -- the thread itself
+// wrote nothing that the leader reads.  The release form costs a cluster-scope fence per stage and
+// made the forwarder loop, not the tensor pipe, set the pace of the pair kernel.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  return remote;
+}
 __device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
                "r"(ncols)
@@ -189,6 +201,7 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
   } else if (warp == 1) {
     if (lane == 0 && rank == 1) {
       // ===================== forwarder (rank 1): my operands are in -> tell the leader ======
+      const uint32_t leader_full = map_to_rank(smem_u32(&ctrl->ring_full[0]), 0);
       int stage = 0;
       uint32_t phase = 0, a_par = 0;
       int prev_rp = -1;
@@ -199,7 +212,7 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
         for (int kb = 0; kb < ga.kb; ++kb) {
           if (RES && new_rp) mbar_wait(smem_u32(&ctrl->a_full[kb]), a_par, ga.err, 9);
           mbar_wait(smem_u32(&ctrl->ring_full[stage]), phase, ga.err, 10);
-          mbar_arrive_cluster(smem_u32(&ctrl->ring_full[stage]), 0);
+          mbar_arrive_cluster_relaxed(leader_full + stage * 8);
           if (++stage == ring_stages) { stage = 0; phase ^= 1; }
         }
         if (new_rp) { a_par ^= 1; prev_rp = rp; }
@@ -271,6 +284,7 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       rt = 2 * rp + (int)rank;
       nt = ng * TU + q % TU;
     };
+    const uint32_t leader_acc_empty = map_to_rank(smem_u32(&ctrl->acc_empty[0]), 0);
     EpiState<EPI> st;
     int rt = 0, nt = 0;
     const bool skip = (ga.debug & 1) != 0;
@@ -300,8 +314,10 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
+        // rank 1: remote arrive without a release fence -- the accumulator reads are complete
+        // (tcgen05.wait::ld) and nothing this warp wrote is read by the leader
         if (rank == 0) mbar_arrive(smem_u32(&ctrl->acc_empty[buf]));
-        else mbar_arrive_cluster(smem_u32(&ctrl->acc_empty[buf]), 0);
+        else mbar_arrive_cluster_relaxed(leader_acc_empty + buf * 8);
       }
     }
   }
