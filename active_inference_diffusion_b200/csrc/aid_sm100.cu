@@ -223,10 +223,11 @@ static int launch_gemm2_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t
   }
   const int a_bytes = RES ? ga.kb * TILE_BYTES : 0;
   const int slot = (RES ? 1 : 2) * TILE_BYTES;
-  int ring = (SMEM_LIMIT - 1024 - SMEM_CTRL - a_bytes) / slot;
+  constexpr int stage_out = gemm2_stage_bytes(EPI);
+  int ring = (SMEM_LIMIT - 1024 - SMEM_CTRL - stage_out - a_bytes) / slot;
   if (ring > MAX_RING2) ring = MAX_RING2;
   if (ring < 2) return fail("gemm2: not enough shared memory for the ring");
-  const size_t smem = 1024 + SMEM_CTRL + a_bytes + (size_t)ring * slot;
+  const size_t smem = 1024 + SMEM_CTRL + stage_out + a_bytes + (size_t)ring * slot;
   const int units = ((ga.row_tiles + 1) / 2) * (ga.n_tiles / 2);
   const int max_pairs = num_sms() / 2;
   const int pairs = units < max_pairs ? units : max_pairs;

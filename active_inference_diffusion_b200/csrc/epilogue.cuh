@@ -43,6 +43,41 @@ __device__ __forceinline__ void group_bar(int bar_id) {
   asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 }
 
+// ---- optional shared-memory staging of output tiles (pair kernels) ---------------------------
+// A packed bf16 k-block tile [8 chunks][128 rows][16 B] and a 32-column block of the tiled fp32
+// layout [8 float4 columns][128 rows][16 B] are both 16 KiB contiguous in global memory and have
+// the same shape, so an epilogue group can assemble one in shared memory (a conflict-free 16-byte
+// st.shared per thread and chunk) and hand it to the TMA engine as ONE bulk store.  With one CTA
+// per tile this lost (the shared-memory port is the bottleneck there); in the CTA-pair kernels the
+// UMMA and the weight refills need 96 instead of 160 B/clk of that port, and taking the stores off
+// the LSU path pays.  STAGED=false keeps direct 16-byte global stores.
+struct Stage {
+  uint32_t base;  // shared-memory address of this group's 16 KiB staging buffer (0: not staged)
+  int bar_id;     // named barrier of the group
+  bool leader;    // the thread that issues (and therefore tracks) the bulk stores
+};
+__device__ __forceinline__ void stage_acquire(const Stage& s) {
+  if (s.leader) bulk_wait_read<0>();   // the previous bulk store has finished reading the buffer
+  group_bar(s.bar_id);
+}
+__device__ __forceinline__ void stage_flush(const Stage& s, void* gdst) {
+  fence_async_smem();
+  group_bar(s.bar_id);
+  if (s.leader) {
+    bulk_s2g(gdst, s.base, TILE_BYTES);
+    bulk_commit();
+  }
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+// 8 consecutive bf16 columns (16-byte chunk `chunk`) of row r into a staged packed tile
+__device__ __forceinline__ void sts_packed8(uint32_t tile_smem, int r, int chunk, const float* y) {
+  sts_v4(tile_smem + chunk * (TILE_M * 16) + r * 16, pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+         pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+}
+
 // Packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE-rn fp32 results per issue slot).
 // The epilogues are bound by the FP32 pipe's issue rate, so the hot math works on register pairs.
 __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
@@ -146,10 +181,10 @@ __device__ __forceinline__ void epi_stage_bias(const EpiArgs& e, float* sb, int 
   }
 }
 
-template <int EPI, int ACT>
+template <int EPI, int ACT, bool STAGED = false>
 __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile, int rt, int nt,
                                            int n_tiles, int r, const float* sb, EpiState<EPI>& st,
-                                           bool has_next, int rt2, int nt2) {
+                                           bool has_next, int rt2, int nt2, const Stage stg = Stage{0, 0, false}) {
   const int row = rt * TILE_M + r;
 
   if constexpr (EPI == EPI_PACK) {
@@ -174,9 +209,16 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
           for (int j = 0; j < 32; ++j) y[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
         }
         const int kb_out = n0 >> 6;
-        if (kb_out < e.out_kb && !(e.debug & 32)) {
+        if (kb_out < e.out_kb && !(e.debug & 32)) {   // uniform over the group
           __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
-          store_packed32(tile, r, n0 & 63, y);
+          if constexpr (STAGED) {
+            if (hb == 0) stage_acquire(stg);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sts_packed8(stg.base, r, hb * 4 + q, y + q * 8);
+            if (hb == 1) stage_flush(stg, tile);
+          } else {
+            store_packed32(tile, r, n0 & 63, y);
+          }
         }
       }
     }
@@ -215,11 +257,20 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
           }
         }
         act_apply32_ct<ACT>(y);
-        if (e.out_tiled && !(e.debug & 32)) {
+        if (e.out_tiled && !(e.debug & 32)) {         // uniform over the group
+          if constexpr (STAGED) {   // 32 columns = 8 float4 columns x 128 rows: one contiguous 16 KiB block
+            stage_acquire(stg);
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            e.out_tiled[((size_t)rt * e.ld4 + (n0 >> 2) + q) * TILE_M + r] =
-                make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+            for (int q = 0; q < 8; ++q)
+              sts_v4(stg.base + q * (TILE_M * 16) + r * 16, __float_as_uint(y[q * 4 + 0]), __float_as_uint(y[q * 4 + 1]),
+                     __float_as_uint(y[q * 4 + 2]), __float_as_uint(y[q * 4 + 3]));
+            stage_flush(stg, e.out_tiled + ((size_t)rt * e.ld4 + (n0 >> 2)) * TILE_M);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              e.out_tiled[((size_t)rt * e.ld4 + (n0 >> 2) + q) * TILE_M + r] =
+                  make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+          }
         }
         if (e.out_packed && (n0 >> 6) < e.out_kb) {
           float yp[32];
@@ -282,6 +333,9 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
     uint32_t rs[16], rh[16];
     tmem_ld16(tmem_tile, rs);                     // scale cols
     tmem_ld16(tmem_tile + 64, rh);                // shift cols
+    if constexpr (STAGED) {
+      if (!(e.debug & 32)) stage_acquire(stg);
+    }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {                 // 16 hidden columns per iteration
       const float4* bsp = reinterpret_cast<const float4*>(sb + c * 16);        // 1 + scale biases
@@ -314,17 +368,25 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
         for (int q = 0; q < 4; ++q)
           st.h[c * 4 + q] = e.h_tiled[((size_t)rt2 * e.h_ld4 + nt2 * 16 + c * 4 + q) * TILE_M + r];
       }
-      if (!(e.debug & 32))
+      if (!(e.debug & 32)) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        uint4 v;
-        v.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
-        v.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
-        v.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
-        v.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
-        const int chunk = c * 2 + q;
-        *reinterpret_cast<uint4*>(tile + chunk * (TILE_M * 8) + r * 8) = v;
+        for (int q = 0; q < 2; ++q) {
+          const int chunk = c * 2 + q;
+          if constexpr (STAGED) {
+            sts_packed8(stg.base, r, chunk, y + q * 8);
+          } else {
+            uint4 v;
+            v.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
+            v.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
+            v.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
+            v.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
+            *reinterpret_cast<uint4*>(tile + chunk * (TILE_M * 8) + r * 8) = v;
+          }
+        }
       }
+    }
+    if constexpr (STAGED) {
+      if (!(e.debug & 32)) stage_flush(stg, tile);
     }
     if (has_next && rt2 != st.rt) {               // LayerNorm statistics change with the row tile only
       modln_stats(e, rt2, r, st.mean, st.rstd);

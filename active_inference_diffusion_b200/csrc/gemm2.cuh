@@ -104,6 +104,19 @@ __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
 
 // RES : A row tile resident in shared memory (kb <= MAX_RES_KB) vs streamed with the B halves.
 // A "pair unit" = (row-tile pair rp, 256-column group ng); rank c owns row tile 2*rp + c.
+// Shared memory reserved for staging output tiles (one 16 KiB buffer per epilogue group) when the
+// build defines AID_STAGE_STORES.  Off by default: measured on B200 it is neutral for the adaLN and
+// attention kernels and slower for the MLP kernels (mlp.0 114 -> 125 us), because the two buffers
+// cost two of the six operand stages.  The GPU suite passes with it on.
+__host__ __device__ constexpr int gemm2_stage_bytes(int epi) {
+#ifdef AID_STAGE_STORES
+  return (epi == EPI_SCORE) ? 0 : 2 * TILE_BYTES;
+#else
+  (void)epi;
+  return 0;
+#endif
+}
+
 template <int EPI, bool RES, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
@@ -114,7 +127,10 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
   const uint32_t base = (raw_addr + 1023u) & ~1023u;          // same offset in both CTAs
   uint8_t* smem = smem_raw + (base - raw_addr);
   Gemm2Ctrl* ctrl = reinterpret_cast<Gemm2Ctrl*>(smem);
-  const uint32_t a_smem = base + SMEM_CTRL;
+  constexpr int STAGE_OUT = gemm2_stage_bytes(EPI);
+  constexpr bool STAGED = STAGE_OUT != 0;
+  const uint32_t out_stage = base + SMEM_CTRL;                 // 2 x 16 KiB (one per epilogue group)
+  const uint32_t a_smem = out_stage + STAGE_OUT;
   const uint32_t ring_smem = a_smem + (RES ? ga.kb * TILE_BYTES : 0);
 
   const int warp = threadIdx.x >> 5;
@@ -251,6 +267,7 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
           const uint64_t ad = umma_desc_kmajor(a_tile, TILE_M * 16);
           const uint64_t bd = umma_desc_kmajor(b_tile, TILE_M * 16);
           if (elect_one()) {
+            if (!(ga.debug & 1024))   // 1024: no MMAs: epilogue-only timing
 #pragma unroll
             for (int k = 0; k < TILE_K / 16; ++k) {
               umma2_bf16(d, ad + (uint64_t)(k * (2 * TILE_M * 16) >> 4), bd + (uint64_t)(k * (2 * TILE_M * 16) >> 4),
@@ -285,6 +302,7 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       nt = ng * TU + q % TU;
     };
     const uint32_t leader_acc_empty = map_to_rank(smem_u32(&ctrl->acc_empty[0]), 0);
+    const Stage stg{STAGED ? out_stage + eg * TILE_BYTES : 0u, 1 + eg, r == 0};
     EpiState<EPI> st;
     int rt = 0, nt = 0;
     const bool skip = (ga.debug & 1) != 0;
@@ -308,7 +326,7 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       tc_fence_after();
       const uint32_t tm = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
       if (!skip) {
-        if (valid) epi_finish<EPI, ACT>(ea, tm, rt, nt, ga.n_tiles, r, sb, st, valid2, rt2, nt2);
+        if (valid) epi_finish<EPI, ACT, STAGED>(ea, tm, rt, nt, ga.n_tiles, r, sb, st, valid2, rt2, nt2, stg);
         else if (valid2) epi_first<EPI>(ea, rt2, nt2, r, st);
       }
       tc_fence_before();
@@ -320,6 +338,7 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
         else mbar_arrive_cluster_relaxed(leader_acc_empty + buf * 8);
       }
     }
+    if (STAGED && stg.leader) bulk_wait_all<0>();   // every staged tile has reached global memory
   }
 
   tc_fence_before();
