@@ -181,10 +181,31 @@ __device__ __forceinline__ void epi_stage_bias(const EpiArgs& e, float* sb, int 
   }
 }
 
+// Early release of the accumulator slot: once the LAST tcgen05.ld of a tile has completed the
+// values are in registers and the MMA warp may overwrite the slot, while this warp still does the
+// math and the stores of the last chunk.  bar = shared::cta address of acc_empty[slot] (remote = 0)
+// or its shared::cluster address in the pair's leader CTA (remote = 1, relaxed arrive: the reads
+// are complete and nothing this warp wrote is consumed through the barrier).
+struct AccRelease {
+  uint32_t bar;
+  int remote;
+};
+__device__ __forceinline__ void acc_release(const AccRelease& rel) {
+  tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    if (rel.remote)
+      asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rel.bar) : "memory");
+    else
+      mbar_arrive(rel.bar);
+  }
+}
+
 template <int EPI, int ACT, bool STAGED = false>
 __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile, int rt, int nt,
                                            int n_tiles, int r, const float* sb, EpiState<EPI>& st,
-                                           bool has_next, int rt2, int nt2, const Stage stg = Stage{0, 0, false}) {
+                                           bool has_next, int rt2, int nt2, const AccRelease rel,
+                                           const Stage stg = Stage{0, 0, false}) {
   const int row = rt * TILE_M + r;
 
   if constexpr (EPI == EPI_PACK) {
@@ -203,6 +224,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
         for (int j = 0; j < 32; j += 2)
           add2(y[j], y[j + 1], __uint_as_float(raw[j]), __uint_as_float(raw[j + 1]));
         if (c + 1 < 4) tmem_ld32(tmem_tile + (c + 1) * 32, raw);   // in flight during this chunk's math
+        else acc_release(rel);                                      // whole tile is in registers
         if (!(e.debug & 64)) act_apply32_ct<ACT>(y);
         if (n0 + 32 > e.n_valid) {
 #pragma unroll
@@ -238,6 +260,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);   // scalar: packed pairs spill here
         if (c + 1 < 4) tmem_ld32(tmem_tile + (c + 1) * 32, raw);   // in flight during this chunk's math
+        else acc_release(rel);                                      // whole tile is in registers
         if (e.resid_tiled && !(e.debug & 128)) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -362,6 +385,8 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
       if (c + 1 < 4) {                            // rs/rh are consumed: next chunk's accumulators
         tmem_ld16(tmem_tile + (c + 1) * 16, rs);
         tmem_ld16(tmem_tile + 64 + (c + 1) * 16, rh);
+      } else {
+        acc_release(rel);                         // whole tile is in registers
       }
       if (has_next && !(e.debug & 128)) {         // refill the consumed registers for the next tile
 #pragma unroll
@@ -455,5 +480,6 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
         }
       }
     }
+    acc_release(rel);
   }
 }

@@ -412,10 +412,9 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       mbar_wait(smem_u32(&ctrl->acc_full[buf]), use & 1, ga.err, 8);
       tc_fence_after();
       const uint32_t tm = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
-      if (!(ga.debug & 1)) epi_finish<EPI, ACT>(ea, tm, rt, nt, ga.n_tiles, r, sb, st, has_next, rt2, nt2);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&ctrl->acc_empty[buf]));
+      const AccRelease rel{smem_u32(&ctrl->acc_empty[buf]), 0};
+      if (!(ga.debug & 1)) epi_finish<EPI, ACT>(ea, tm, rt, nt, ga.n_tiles, r, sb, st, has_next, rt2, nt2, rel);
+      else acc_release(rel);
     }
   }
 

@@ -325,17 +325,12 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       mbar_wait(smem_u32(&ctrl->acc_full[buf]), use & 1, ga.err, 8);
       tc_fence_after();
       const uint32_t tm = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
-      if (!skip) {
-        if (valid) epi_finish<EPI, ACT, STAGED>(ea, tm, rt, nt, ga.n_tiles, r, sb, st, valid2, rt2, nt2, stg);
-        else if (valid2) epi_first<EPI>(ea, rt2, nt2, r, st);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        // rank 1: remote arrive without a release fence -- the accumulator reads are complete
-        // (tcgen05.wait::ld) and nothing this warp wrote is read by the leader
-        if (rank == 0) mbar_arrive(smem_u32(&ctrl->acc_empty[buf]));
-        else mbar_arrive_cluster_relaxed(leader_acc_empty + buf * 8);
+      const AccRelease rel{rank == 0 ? smem_u32(&ctrl->acc_empty[buf]) : leader_acc_empty + buf * 8, rank != 0};
+      if (!skip && valid) {
+        epi_finish<EPI, ACT, STAGED>(ea, tm, rt, nt, ga.n_tiles, r, sb, st, valid2, rt2, nt2, rel, stg);
+      } else {
+        acc_release(rel);
+        if (!skip && valid2) epi_first<EPI>(ea, rt2, nt2, r, st);
       }
     }
     if (STAGED && stg.leader) bulk_wait_all<0>();   // every staged tile has reached global memory
