@@ -7,8 +7,7 @@ for row in csv.DictReader(lines):
     v = float(row["Metric Value"].replace(",", ""))
     unit = row["Metric Unit"]
     v = v / 1e3 if unit in ("ns", "nsecond") else (v * 1e3 if unit in ("ms", "msecond") else v)
-    m = re.search(r"gemm_kernel<\(int\)(\d), \(int\)(\d), \(int\)(\d), \(bool\)(\d)>", name) or re.search(r"gemm_kernel<(\d), (\d), (\d), (\w+)>", name)
-    key = f"gemm<epi={m.group(1)},NW={m.group(2)},G={m.group(3)},res={m.group(4)}>" if m else name.split("(")[0][-44:]
+    key = name.split("(")[0][-44:]
     agg[key][0] += 1
     agg[key][1] += v
 tot = sum(v[1] for v in agg.values())
