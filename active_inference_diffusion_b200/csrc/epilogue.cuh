@@ -353,21 +353,38 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
     // rows already holds 1 + b (k_pack_bias), so one output costs 2 FADD + 2 FFMA.
     const float rstd = st.rstd, nmr = -st.mean * st.rstd;
     __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + nt) * TILE_ELEMS;
-    uint32_t rs[16], rh[16];
-    tmem_ld16(tmem_tile, rs);                     // scale cols
-    tmem_ld16(tmem_tile + 64, rh);                // shift cols
+    // 8 chunks of 8 hidden columns, TMEM loads double-buffered one chunk ahead: the math of a chunk
+    // is short (8 packed instructions), so a single-buffered load -> wait -> math chain left the
+    // warps waiting on tcgen05.ld most of the time.
+    uint32_t rs[2][8], rh[2][8];
+    tmem_ld8(tmem_tile, rs[0]);                   // scale cols
+    tmem_ld8(tmem_tile + 64, rh[0]);              // shift cols
+    // LayerNorm statistics change with the row tile only; when the next tile starts a new row tile
+    // its partials are fetched NOW and merged after this tile's work (ncu: the un-prefetched loads
+    // were ~18 % of the adaLN epilogue's stall samples).
+    const bool new_stats = has_next && rt2 != st.rt;
+    float2 sp[4];
+    if (new_stats) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        sp[p] = (p < e.stats_nt) ? e.stats_in[((size_t)rt2 * e.stats_nt + p) * TILE_M + r] : make_float2(0.f, 0.f);
+    }
     if constexpr (STAGED) {
       if (!(e.debug & 32)) stage_acquire(stg);
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {                 // 16 hidden columns per iteration
-      const float4* bsp = reinterpret_cast<const float4*>(sb + c * 16);        // 1 + scale biases
-      const float4* bhp = reinterpret_cast<const float4*>(sb + 64 + c * 16);   // shift biases
-      float y[16];
-      tmem_ld_wait();
+    for (int c = 0; c < 8; ++c) {                 // 8 hidden columns = one 16-byte output chunk
+      const float4* bsp = reinterpret_cast<const float4*>(sb + c * 8);        // 1 + scale biases
+      const float4* bhp = reinterpret_cast<const float4*>(sb + 64 + c * 8);   // shift biases
+      float y[8];
+      tmem_ld_wait();                             // chunk c (and nothing else) is outstanding
+      if (c + 1 < 8) {
+        tmem_ld8(tmem_tile + (c + 1) * 8, rs[(c + 1) & 1]);
+        tmem_ld8(tmem_tile + 64 + (c + 1) * 8, rh[(c + 1) & 1]);
+      }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 hv = st.h[c * 4 + q];
+      for (int q = 0; q < 2; ++q) {
+        const float4 hv = st.h[c * 2 + q];
         const float4 b1 = bsp[q], b2 = bhp[q];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {             // two hidden columns per packed instruction
@@ -375,46 +392,51 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
           const float2 hx = i ? make_float2(hv.z, hv.w) : make_float2(hv.x, hv.y);
           const float2 bs = i ? make_float2(b1.z, b1.w) : make_float2(b1.x, b1.y);
           const float2 bh = i ? make_float2(b2.z, b2.w) : make_float2(b2.x, b2.y);
-          const float2 scale1 = __fadd2_rn(make_float2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), bs);
-          const float2 shift = __fadd2_rn(make_float2(__uint_as_float(rh[j]), __uint_as_float(rh[j + 1])), bh);
+          const float2 scale1 = __fadd2_rn(make_float2(__uint_as_float(rs[c & 1][j]), __uint_as_float(rs[c & 1][j + 1])), bs);
+          const float2 shift = __fadd2_rn(make_float2(__uint_as_float(rh[c & 1][j]), __uint_as_float(rh[c & 1][j + 1])), bh);
           const float2 hn = __ffma2_rn(hx, make_float2(rstd, rstd), make_float2(nmr, nmr));
           const float2 o = __ffma2_rn(hn, scale1, shift);
           y[j] = o.x; y[j + 1] = o.y;
         }
       }
-      if (c + 1 < 4) {                            // rs/rh are consumed: next chunk's accumulators
-        tmem_ld16(tmem_tile + (c + 1) * 16, rs);
-        tmem_ld16(tmem_tile + 64 + (c + 1) * 16, rh);
-      } else {
-        acc_release(rel);                         // whole tile is in registers
+      if (c == 6) {
+        // chunk 7's loads were issued above; wait for them here so the slot can be released one
+        // chunk early (its values are then in registers)
+        tmem_ld_wait();
+        acc_release(rel);
       }
       if (has_next && !(e.debug & 128)) {         // refill the consumed registers for the next tile
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          st.h[c * 4 + q] = e.h_tiled[((size_t)rt2 * e.h_ld4 + nt2 * 16 + c * 4 + q) * TILE_M + r];
+        for (int q = 0; q < 2; ++q)
+          st.h[c * 2 + q] = e.h_tiled[((size_t)rt2 * e.h_ld4 + nt2 * 16 + c * 2 + q) * TILE_M + r];
       }
       if (!(e.debug & 32)) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int chunk = c * 2 + q;
-          if constexpr (STAGED) {
-            sts_packed8(stg.base, r, chunk, y + q * 8);
-          } else {
-            uint4 v;
-            v.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
-            v.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
-            v.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
-            v.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
-            *reinterpret_cast<uint4*>(tile + chunk * (TILE_M * 8) + r * 8) = v;
-          }
+        if constexpr (STAGED) {
+          sts_packed8(stg.base, r, c, y);
+        } else {
+          uint4 v;
+          v.x = pack_bf16x2(y[0], y[1]);
+          v.y = pack_bf16x2(y[2], y[3]);
+          v.z = pack_bf16x2(y[4], y[5]);
+          v.w = pack_bf16x2(y[6], y[7]);
+          *reinterpret_cast<uint4*>(tile + c * (TILE_M * 8) + r * 8) = v;
         }
       }
     }
     if constexpr (STAGED) {
       if (!(e.debug & 32)) stage_flush(stg, tile);
     }
-    if (has_next && rt2 != st.rt) {               // LayerNorm statistics change with the row tile only
-      modln_stats(e, rt2, r, st.mean, st.rstd);
+    if (new_stats) {
+      float sn = 0.f, m = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (p < e.stats_nt) stats_merge(sn, m, m2, (float)min(TILE_N, e.h_dim - p * TILE_N), sp[p].x, sp[p].y);
+      for (int p = 4; p < e.stats_nt; ++p) {      // hidden widths beyond 512: not prefetched
+        const float2 s2 = e.stats_in[((size_t)rt2 * e.stats_nt + p) * TILE_M + r];
+        stats_merge(sn, m, m2, (float)min(TILE_N, e.h_dim - p * TILE_N), s2.x, s2.y);
+      }
+      st.mean = m;
+      st.rstd = rsqrtf(m2 / (float)e.h_dim + 1e-5f);
       st.rt = rt2;
     }
   } else {  // EPI_SCORE
