@@ -12,6 +12,7 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
+#include "chain2.cuh"
 
 using namespace aid;
 
@@ -292,6 +293,65 @@ static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs e
     }
   } else {
     return launch_gemm_shape<EPI, ACT_NONE>(ga, ea, st, res, wide);
+  }
+}
+
+// adaLN modulation -> next layer in one CTA-pair kernel (chain2.cuh), opt-in with AID_CHAIN=1.
+// Correct (the GPU suite passes with it) and it removes the 134 MB xn round trip per layer pair, but
+// in its first form it is slower than the two separate kernels (3.65 vs 3.15 ms per denoise step at
+// 65,536 rows): the two epilogues in one kernel spill at 168 registers and phase 1 has only three
+// k-blocks of operands in flight.  Kept as the starting point of the cross-layer fusion work.
+static bool use_chain() {
+  static const bool on = use_pairs() && getenv("AID_CHAIN") && atoi(getenv("AID_CHAIN")) != 0;
+  return on;
+}
+static unsigned g_chain_flip = 0;
+
+template <int EPI2, int ACT2>
+static int launch_chain_inst(const ChainArgs& ca, const EpiArgs& e1, const EpiArgs& e2, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = chain2_kernel<EPI2, ACT2>;
+  if (!configured) {
+    AID_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    configured = true;
+  }
+  const size_t smem = 1024 + SMEM_CTRL + (size_t)ca.kb * TILE_BYTES + (size_t)CHAIN_RING * TILE_BYTES;
+  const int rps = (ca.row_tiles + 1) / 2;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = rps < max_pairs ? rps : max_pairs;
+  if (pairs < 1) return 0;
+  kern<<<2 * pairs, GEMM_THREADS, smem, st>>>(ca, e1, e2);
+  AID_LAUNCH_CHECK("chain2_kernel");
+  return 0;
+}
+
+// mod: adaLN modulation weight (MODLN row map), w2: the layer that consumes the normalised tile
+static bool chain_ok(const PLin& mod, const PLin& w2) {
+  return use_chain() && mod.nw == 1 && w2.nw == 1 && mod.kb <= MAX_RES_KB && mod.kb % 2 == 0 &&
+         mod.n_tiles == mod.kb && w2.kb == mod.kb && w2.n_tiles % 2 == 0;
+}
+
+template <int EPI2>
+static int launch_chain(const uint8_t* csilu, int row_tiles, const PLin& mod, const PLin& w2, EpiArgs e1,
+                        EpiArgs e2, cudaStream_t st, int* err_flag) {
+  static const int dbg = getenv("AID_DEBUG") ? atoi(getenv("AID_DEBUG")) : 0;
+  ChainArgs ca;
+  ca.A = csilu; ca.B1 = mod.w; ca.B2 = w2.w;
+  ca.row_tiles = row_tiles; ca.kb = mod.kb; ca.n_tiles2 = w2.n_tiles;
+  ca.err = err_flag; ca.debug = dbg;
+  ca.reverse = (dbg & 8) ? 0 : (int)(g_chain_flip++ & 1);
+  e1.debug = dbg; e2.debug = dbg;
+  e1.split_rt = row_tiles; e2.split_rt = row_tiles;
+  if (!e1.bias) e1.bias = mod.b;
+  if (!e2.bias) e2.bias = w2.b;
+  if constexpr (EPI2 == EPI_PACK) {
+    switch (e2.act) {
+      case ACT_SILU: return launch_chain_inst<EPI2, ACT_SILU>(ca, e1, e2, st);
+      case ACT_GELU: return launch_chain_inst<EPI2, ACT_GELU>(ca, e1, e2, st);
+      default: return fail("launch_chain: unsupported activation");
+    }
+  } else {
+    return launch_chain_inst<EPI2, ACT_NONE>(ca, e1, e2, st);
   }
 }
 
@@ -600,21 +660,45 @@ static int run_score_trunk(const ScoreW& s, ScoreWS& w, const StepOut& o, cudaSt
     return launch_gemm<EPI_MODLN>(cs, w.RT, lin, e, st, w.err);
   };
 
+  auto modln_args = [&]() {
+    EpiArgs e = epi_zero();
+    e.rows_valid = w.B; e.n_valid = 2 * H; e.out_packed = w.xn; e.out_kb = H / 64;
+    e.h_tiled = w.h; e.h_ld4 = ld4; e.stats_in = w.h_stats; e.stats_nt = nt_h; e.h_dim = H;
+    return e;
+  };
+  auto f32_args = [&](bool resid) {
+    EpiArgs e = epi_zero();
+    e.n_valid = H; e.rows_valid = w.B; e.out_tiled = w.h; e.ld4 = ld4; e.stats_out = w.h_stats;
+    e.resid_tiled = resid ? w.h : nullptr;
+    return e;
+  };
   AID_TRY(f32_out(s.lp, zp, false));
   for (int i = 0; i < s.NB; ++i) {
     const ScoreBlockW& b = s.blk[i];
-    AID_TRY(modln(b.mod1));
-    AID_TRY(f32_out(b.attn, xn, true));
-    AID_TRY(modln(b.mod2));
+    if (chain_ok(b.mod1, b.attn)) {
+      AID_TRY(launch_chain<EPI_F32>(cs, w.RT, b.mod1, b.attn, modln_args(), f32_args(true), st, w.err));
+    } else {
+      AID_TRY(modln(b.mod1));
+      AID_TRY(f32_out(b.attn, xn, true));
+    }
     EpiArgs e = epi_zero();
     e.act = ACT_GELU; e.n_valid = 4 * H; e.rows_valid = w.B; e.out_packed = w.act; e.out_kb = 4 * H / 64;
-    AID_TRY(launch_gemm<EPI_PACK>(xn, w.RT, b.fc1, e, st, w.err));
+    if (chain_ok(b.mod2, b.fc1)) {
+      AID_TRY(launch_chain<EPI_PACK>(cs, w.RT, b.mod2, b.fc1, modln_args(), e, st, w.err));
+    } else {
+      AID_TRY(modln(b.mod2));
+      AID_TRY(launch_gemm<EPI_PACK>(xn, w.RT, b.fc1, e, st, w.err));
+    }
     AID_TRY(f32_out(b.fc2, reinterpret_cast<uint8_t*>(w.act), true));
   }
-  AID_TRY(modln(s.nf));
   EpiArgs e = epi_zero();
   e.act = ACT_SILU; e.n_valid = H / 2; e.rows_valid = w.B; e.out_packed = w.o1; e.out_kb = ceil_div(H / 2, 64);
-  AID_TRY(launch_gemm<EPI_PACK>(xn, w.RT, s.out0, e, st, w.err));
+  if (chain_ok(s.nf, s.out0)) {
+    AID_TRY(launch_chain<EPI_PACK>(cs, w.RT, s.nf, s.out0, modln_args(), e, st, w.err));
+  } else {
+    AID_TRY(modln(s.nf));
+    AID_TRY(launch_gemm<EPI_PACK>(xn, w.RT, s.out0, e, st, w.err));
+  }
   e = epi_zero();
   e.bias = nullptr;  // output_proj.2 has no bias; launch_gemm substitutes the zero-padded vector
   e.n_valid = s.L; e.rows_valid = w.B;

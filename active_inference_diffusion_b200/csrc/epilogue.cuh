@@ -50,7 +50,9 @@ __device__ __forceinline__ void group_bar(int bar_id) {
 // st.shared per thread and chunk) and hand it to the TMA engine as ONE bulk store.  With one CTA
 // per tile this lost (the shared-memory port is the bottleneck there); in the CTA-pair kernels the
 // UMMA and the weight refills need 96 instead of 160 B/clk of that port, and taking the stores off
-// the LSU path pays.  STAGED=false keeps direct 16-byte global stores.
+// the LSU path pays.  SMODE 0 = direct 16-byte global stores; 1 = assemble + TMA bulk store;
+// 2 = assemble in shared memory only (the tile is the next GEMM's A operand, chain2.cuh: the
+// caller owns the synchronisation).
 struct Stage {
   uint32_t base;  // shared-memory address of this group's 16 KiB staging buffer (0: not staged)
   int bar_id;     // named barrier of the group
@@ -201,7 +203,7 @@ __device__ __forceinline__ void acc_release(const AccRelease& rel) {
   }
 }
 
-template <int EPI, int ACT, bool STAGED = false>
+template <int EPI, int ACT, int SMODE = 0>
 __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile, int rt, int nt,
                                            int n_tiles, int r, const float* sb, EpiState<EPI>& st,
                                            bool has_next, int rt2, int nt2, const AccRelease rel,
@@ -233,7 +235,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
         const int kb_out = n0 >> 6;
         if (kb_out < e.out_kb && !(e.debug & 32)) {   // uniform over the group
           __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
-          if constexpr (STAGED) {
+          if constexpr (SMODE == 1) {
             if (hb == 0) stage_acquire(stg);
 #pragma unroll
             for (int q = 0; q < 4; ++q) sts_packed8(stg.base, r, hb * 4 + q, y + q * 8);
@@ -281,7 +283,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
         }
         act_apply32_ct<ACT>(y);
         if (e.out_tiled && !(e.debug & 32)) {         // uniform over the group
-          if constexpr (STAGED) {   // 32 columns = 8 float4 columns x 128 rows: one contiguous 16 KiB block
+          if constexpr (SMODE == 1) {   // 32 columns = 8 float4 columns x 128 rows: one contiguous 16 KiB block
             stage_acquire(stg);
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -369,7 +371,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
       for (int p = 0; p < 4; ++p)
         sp[p] = (p < e.stats_nt) ? e.stats_in[((size_t)rt2 * e.stats_nt + p) * TILE_M + r] : make_float2(0.f, 0.f);
     }
-    if constexpr (STAGED) {
+    if constexpr (SMODE == 1) {
       if (!(e.debug & 32)) stage_acquire(stg);
     }
 #pragma unroll
@@ -411,7 +413,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
           st.h[c * 2 + q] = e.h_tiled[((size_t)rt2 * e.h_ld4 + nt2 * 16 + c * 2 + q) * TILE_M + r];
       }
       if (!(e.debug & 32)) {
-        if constexpr (STAGED) {
+        if constexpr (SMODE != 0) {
           sts_packed8(stg.base, r, c, y);
         } else {
           uint4 v;
@@ -423,7 +425,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
         }
       }
     }
-    if constexpr (STAGED) {
+    if constexpr (SMODE == 1) {
       if (!(e.debug & 32)) stage_flush(stg, tile);
     }
     if (new_stats) {

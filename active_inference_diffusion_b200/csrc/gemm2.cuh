@@ -327,7 +327,7 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       const uint32_t tm = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
       const AccRelease rel{rank == 0 ? smem_u32(&ctrl->acc_empty[buf]) : leader_acc_empty + buf * 8, rank != 0};
       if (!skip && valid) {
-        epi_finish<EPI, ACT, STAGED>(ea, tm, rt, nt, ga.n_tiles, r, sb, st, valid2, rt2, nt2, rel, stg);
+        epi_finish<EPI, ACT, STAGED ? 1 : 0>(ea, tm, rt, nt, ga.n_tiles, r, sb, st, valid2, rt2, nt2, rel, stg);
       } else {
         acc_release(rel);
         if (!skip && valid2) epi_first<EPI>(ea, rt2, nt2, r, st);

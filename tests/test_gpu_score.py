@@ -160,3 +160,28 @@ def test_full_size_rows_are_independent_and_shardable():
             assert torch.equal(part, full[sl]), lo
     assert torch.isfinite(full).all()
     assert float(full.std()) > 1e-3
+
+
+@pytest.mark.parametrize("env", [{"AID_CHAIN": "1"}, {"AID_PAIRS": "0"}])
+def test_alternative_kernel_families_subprocess(env):
+    """The opt-in kernel families (read once per process from the environment): AID_CHAIN=1 = adaLN ->
+    next-layer chain kernel (normalised tile handed over in shared memory), AID_PAIRS=0 = single-CTA
+    kernels.  Both must reproduce the oracle's reverse diffusion within the same bound."""
+    import os, subprocess, sys
+    code = ("import torch\n"
+            "from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess\n"
+            "from oracle import restatement as R\n"
+            "from tests.util import gen, make_score_net, rel_l2\n"
+            "L, O, H, NB, T, B = 128, 17, 512, 6, 4, 300\n"
+            "net, params = make_score_net(L, O, H, NB, device='cuda')\n"
+            "diff = LatentDiffusionProcess(DiffusionConfig(num_diffusion_steps=T), L).cuda()\n"
+            "g = gen(3); obs = torch.randn(B, O, generator=g); zT = torch.randn(B, L, generator=g)\n"
+            "noise = torch.randn(T - 1, B, L, generator=g)\n"
+            "with torch.no_grad():\n"
+            "    want = R.generate_latent_trajectory(params, R.make_schedule(T), zT, obs, list(noise))[-1]\n"
+            "    got = diff.generate_latent_trajectory(net, B, obs.cuda(), z_init=zT.cuda(), noise=noise.cuda())[-1]\n"
+            "e = rel_l2(got, want); print(e); assert e < 2e-2, e\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), cwd=root, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
