@@ -236,7 +236,20 @@ static int launch_gemm2_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t
   const bool prof = g_prof.on && g_prof.epi == EPI && g_prof.kb == ga.kb && g_prof.n_tiles == ga.n_tiles &&
                     g_prof.used < 200000;
   if (prof) cudaEventRecord(prof_event(), st);
-  kern<<<2 * pairs, GEMM_THREADS, smem, st>>>(ga, ea, ring);
+  {
+    static const bool pdl = !(getenv("AID_DEBUG") && (atoi(getenv("AID_DEBUG")) & 2048));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);        // cluster dims (2,1,1) come from the kernel's __cluster_dims__
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && !prof) ? 1 : 0;
+    AID_CHECK(cudaLaunchKernelEx(&cfg, kern, ga, ea, ring));
+  }
   if (prof) cudaEventRecord(prof_event(), st);
   AID_LAUNCH_CHECK("gemm2_kernel");
   return 0;

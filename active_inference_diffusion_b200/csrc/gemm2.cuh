@@ -165,10 +165,12 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
     tmem_alloc2(smem_u32(&ctrl->tmem_base), 512);
     tmem_relinquish2();
   }
+  pdl_launch_dependents();                                    // see gemm.cuh: prologue overlaps the previous kernel's tail
   tc_fence_before();
   cluster_sync_all();                                         // barriers of BOTH CTAs are live
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
+  pdl_wait();                                                 // nothing above touched global memory
 
   auto unit_coords = [&](int u, int& rp, int& ng) {
     const int ue = ga.reverse ? num_units - 1 - u : u;
