@@ -9,8 +9,9 @@ from .heads import DiffusionConditionedPolicy, LatentDynamicsModel, ValueNetwork
 from .active_inference import DiffusionActiveInference
 from .pipeline import CandidateScorer
 from .belief_dynamics import BeliefDynamics, FreeEnergyComputation
+from .visual_encoder import DrQV2Encoder, SpatialAttention
 
 __all__ = ["ActiveInferenceConfig", "BeliefDynamicsConfig", "DiffusionConfig",
            "LatentDiffusionProcess", "LatentScoreNetwork", "DiffusionConditionedPolicy",
            "LatentDynamicsModel", "ValueNetwork", "DiffusionActiveInference", "CandidateScorer",
-           "BeliefDynamics", "FreeEnergyComputation"]
+           "BeliefDynamics", "FreeEnergyComputation", "DrQV2Encoder", "SpatialAttention"]

@@ -26,6 +26,12 @@ class AidHeadsDims(ctypes.Structure):
                 ("time_embed_dim", c_int32)]
 
 
+class AidEncoderDims(ctypes.Structure):
+    _fields_ = [("in_channels", c_int32), ("height", c_int32), ("width", c_int32),
+                ("num_filters", c_int32), ("num_layers", c_int32), ("feature_dim", c_int32),
+                ("use_attention", c_int32), ("precision", c_int32)]
+
+
 class AidEfeConfig(ctypes.Structure):
     _fields_ = [("epistemic_weight", c_float), ("pragmatic_weight", c_float),
                 ("consistency_weight", c_float), ("discount_factor", c_float)]
@@ -117,6 +123,21 @@ def _declare_misc(l: ctypes.CDLL) -> None:
     l.aid_time_importance_update.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]
 
 
+def _declare_encoder(l: ctypes.CDLL) -> None:
+    D = POINTER(AidEncoderDims)
+    l.aid_encoder_packed_bytes.restype = c_size_t
+    l.aid_encoder_packed_bytes.argtypes = [D]
+    l.aid_encoder_num_params.restype = c_int32
+    l.aid_encoder_num_params.argtypes = [D]
+    l.aid_encoder_pack.restype = c_int32
+    l.aid_encoder_pack.argtypes = [D, POINTER(c_void_p), c_int32, c_void_p, c_size_t, c_void_p]
+    l.aid_encoder_workspace_bytes.restype = c_size_t
+    l.aid_encoder_workspace_bytes.argtypes = [D, c_int32]
+    l.aid_encoder_forward.restype = c_int32
+    l.aid_encoder_forward.argtypes = [D, c_void_p, c_void_p, c_size_t, c_int32, c_void_p, c_int32, c_void_p,
+                                      c_void_p]
+
+
 def lib() -> ctypes.CDLL:
     """Load the CUDA extension; fail loudly when it has not been built."""
     global _lib
@@ -129,6 +150,7 @@ def lib() -> ctypes.CDLL:
         _declare(l)
         _declare_train(l)
         _declare_misc(l)
+        _declare_encoder(l)
         _lib = l
     return _lib
 

@@ -1039,6 +1039,7 @@ extern "C" int32_t aid_gemm_nt(const float* a, int64_t a_rs, int64_t a_cs, const
 
 #include "heads.inc"
 #include "belief.inc"
+#include "encoder.inc"
 
 // ------------------------------------------------------------------------------------------
 extern "C" int32_t aid_abi_version(void) { return AID_ABI_VERSION; }

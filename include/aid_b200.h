@@ -210,6 +210,40 @@ int32_t aid_fp_belief_update(const double* mean, const double* variance, const d
 int32_t aid_time_importance_update(const float* t, const float* loss, int32_t n, float* weights,
                                    int32_t n_bins, int64_t* bins_out, void* stream);
 
+/* ---- DrQV2Encoder.forward — encoder/visual_encoders.py:13-189 (+ SpatialAttention :192-224) ---
+ * SURVEY.md §8 f-1.  Eval-mode forward: 3x3 convs (first stride 2) with spectral-norm scaling
+ * W/sigma, sigma = u^T W v from the stored buffers (no power iteration), GroupNorm(min(32,C/4)) +
+ * Mish, spatial attention x*(1+sigmoid(conv7x7([mean_c, max_c])/temperature)), flatten,
+ * LayerNorm(D), Linear(D,2F), LayerNorm, Mish, Linear(2F,F), LayerNorm, tanh.  Dropout = identity.
+ * Convolutions and the D->2F projection run on the tcgen05 GEMM kernels (bf16 operands, fp32
+ * accumulation; precision 1 = bf16x3 operand split, fp32-grade).
+ * params (aid_encoder_pack), device fp32 pointers in this order:
+ *   per conv layer i: convs.i.weight_orig [Cout,Cin,3,3], convs.i.weight_u [Cout] (NULL: no spectral
+ *   norm), convs.i.weight_v [Cin*9] (NULL likewise), norms.i.weight [Cout], norms.i.bias [Cout];
+ *   attention.spatial_conv.weight [1,2,7,7], .bias [1], attention.temperature [1] (NULL when
+ *   use_attention == 0); ln.weight [D], ln.bias [D]; output_layers.0.weight [2F,D], .bias [2F];
+ *   output_layers.1.weight/.bias [2F]; output_layers.4.weight [F,2F], .bias [F];
+ *   output_layers.5.weight/.bias [F].
+ * pixels: [batch, in_channels, height, width] contiguous, uint8 (scaled by 1/255 as :165-166) when
+ * is_u8 != 0, else fp32.  features: [batch, feature_dim] fp32. */
+typedef struct AidEncoderDims {
+  int32_t in_channels;   /* channels x frame_stack */
+  int32_t height, width;
+  int32_t num_filters;   /* multiple of 8; layer i has num_filters * 2^min(i,3) channels */
+  int32_t num_layers;
+  int32_t feature_dim;
+  int32_t use_attention;
+  int32_t precision;     /* 0 bf16, 1 bf16x3 (fixed at pack time) */
+} AidEncoderDims;
+size_t aid_encoder_packed_bytes(const AidEncoderDims* dims);
+int32_t aid_encoder_num_params(const AidEncoderDims* dims);
+int32_t aid_encoder_pack(const AidEncoderDims* dims, const float* const* params, int32_t num_params,
+                         void* packed, size_t packed_bytes, void* stream);
+size_t aid_encoder_workspace_bytes(const AidEncoderDims* dims, int32_t batch);
+int32_t aid_encoder_forward(const AidEncoderDims* dims, const void* packed, void* workspace,
+                            size_t workspace_bytes, int32_t batch, const void* pixels, int32_t is_u8,
+                            float* features, void* stream);
+
 /* ---- primitive exposed for tests: y = act(x W^T + b) through the tcgen05 path --------------
  * x [M,K], w [N,K], bias [N] or NULL, y [M,N]; act: 0 none, 1 SiLU, 2 ReLU, 3 GELU(erf).
  * via_packed != 0 routes the result through the bf16 packed epilogue and back (tests EPI_PACK). */

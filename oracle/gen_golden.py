@@ -153,6 +153,31 @@ def gen_misc(name):
     print(name, float(f))
 
 
+def gen_encoder(name, obs_shape, frame_stack, feature_dim, num_filters, B, use_attention=True):
+    """DrQV2Encoder (encoder/visual_encoders.py) at a size whose weights fit a fixture: the
+    architecture is parametric in num_filters / feature_dim / image size."""
+    from active_inference_diffusion.encoder.visual_encoders import DrQV2Encoder
+    torch.manual_seed(5)
+    enc = DrQV2Encoder(obs_shape, feature_dim=feature_dim, frame_stack=frame_stack, num_filters=num_filters,
+                       use_attention=use_attention)
+    raw_sd = {k: v.clone() for k, v in enc.state_dict().items()}
+    enc.load_state_dict(perturb_generic(enc.state_dict(), 31, 0.05))
+    enc.eval()
+    g = torch.Generator().manual_seed(17)
+    c, h, w = obs_shape
+    u8 = torch.randint(0, 256, (B, frame_stack * c, h, w), generator=g, dtype=torch.uint8)
+    f32 = torch.rand(B, frame_stack, c, h, w, generator=g)          # 5-D, separate frames
+    single = torch.rand(B, c, h, w, generator=g)                      # one frame, repeated by the encoder
+    with torch.no_grad():
+        outs = {"u8": enc(u8), "f32_5d": enc(f32), "single_frame": enc(single)}
+    torch.save({"dims": dict(obs_shape=obs_shape, frame_stack=frame_stack, feature_dim=feature_dim,
+                             num_filters=num_filters, B=B, use_attention=use_attention),
+                "seed": 5, "init_state": raw_sd, "weights": {k: v.clone() for k, v in enc.state_dict().items()},
+                "inputs": {"u8": u8, "f32_5d": f32, "single_frame": single}, "outputs": outs},
+               os.path.join(OUT, f"{name}.pt"))
+    print(name, "features max", float(outs["u8"].abs().max()), "conv_out_dim", enc.conv_out_dim)
+
+
 def main():
     import_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -161,6 +186,8 @@ def main():
     gen_score_and_sampler("score_default_dims", 128, 17, 512, 6, 50, 8, "cosine", False)
     gen_active_inference("active_inference_small", 32, 6, 64, 6, 9)
     gen_misc("free_energy_belief")
+    gen_encoder("encoder_small", (3, 12, 12), 3, 16, 8, 5)
+    gen_encoder("encoder_small_odd", (1, 11, 14), 2, 8, 8, 3, use_attention=False)
 
 
 if __name__ == "__main__":

@@ -594,3 +594,69 @@ def belief_update_full(mean: np.ndarray, cov: np.ndarray, observation: np.ndarra
     S = V @ torch.diag(w) @ V.T
     P = torch.linalg.inv(S + min_eig * torch.eye(L, dtype=torch.float64))
     return new_mean, S.numpy(), P.numpy()
+
+
+# --------------------------------------------------------------------------
+# DrQ-v2 visual encoder — encoder/visual_encoders.py, eval mode
+# --------------------------------------------------------------------------
+
+def spectral_weight(p: Params, name: str) -> torch.Tensor:
+    """Weight of a spectral-normed conv in eval mode: weight_orig / (u . (W_mat v)) with the stored
+    u, v and no power iteration (torch.nn.utils.spectral_norm, applied at visual_encoders.py:70-71).
+    A conv built without spectral norm has a plain `weight`."""
+    if name + ".weight_orig" not in p:
+        return p[name + ".weight"]
+    w = p[name + ".weight_orig"]
+    sigma = torch.dot(p[name + ".weight_u"], torch.mv(w.reshape(w.shape[0], -1), p[name + ".weight_v"]))
+    return w / sigma
+
+
+def encoder_num_layers(p: Params) -> int:
+    n = 0
+    while f"norms.{n}.weight" in p:
+        n += 1
+    return n
+
+
+def spatial_attention(p: Params, x: torch.Tensor) -> torch.Tensor:
+    """visual_encoders.py:210-224: x + x * sigmoid(conv7x7([mean_c, max_c]) / temperature)."""
+    pooled = torch.cat([x.mean(dim=1, keepdim=True), x.max(dim=1, keepdim=True)[0]], dim=1)
+    logits = F.conv2d(pooled, p["attention.spatial_conv.weight"], p["attention.spatial_conv.bias"], padding=3)
+    return x + x * torch.sigmoid(logits / p["attention.temperature"])
+
+
+def encoder_canonical_input(x: torch.Tensor, base_channels: int, frame_stack: int) -> torch.Tensor:
+    """Input conventions of visual_encoders.py:149-166 (frame axis folding, single-frame repeat,
+    uint8 -> [0,1])."""
+    if x.dim() == 5:
+        b, t, c, h, w = x.shape
+        x = x.reshape(b, t * c, h, w)
+    elif x.dim() == 4:
+        if x.shape[1] == base_channels and frame_stack > 1:
+            x = x.repeat(1, frame_stack, 1, 1)
+    elif x.dim() == 3:
+        x = x.unsqueeze(0)
+    if x.dtype == torch.uint8:
+        x = x.float() / 255.0
+    return x
+
+
+def encoder_forward(p: Params, x: torch.Tensor, return_intermediates: bool = False):
+    """DrQV2Encoder.forward, visual_encoders.py:136-189, on an already canonical float input
+    [B, C*frames, H, W]: conv(3x3, stride 2 then 1, no bias) -> GroupNorm -> Mish per layer
+    (Dropout2d is the identity in eval), spatial attention, flatten (channel-major), LayerNorm,
+    Linear -> LayerNorm -> Mish -> Linear -> LayerNorm -> tanh."""
+    inter = {}
+    n_layers = encoder_num_layers(p)
+    for i in range(n_layers):
+        x = F.conv2d(x, spectral_weight(p, f"convs.{i}"), None, stride=2 if i == 0 else 1, padding=1)
+        gw = p[f"norms.{i}.weight"]
+        x = F.mish(F.group_norm(x, min(32, gw.shape[0] // 4), gw, p[f"norms.{i}.bias"], 1e-5))
+        inter[f"conv{i}"] = x
+    if "attention.spatial_conv.weight" in p:
+        x = spatial_attention(p, x)
+    x = layer_norm(p, "ln", x.reshape(x.shape[0], -1))
+    inter["ln"] = x
+    x = F.mish(layer_norm(p, "output_layers.1", linear(p, "output_layers.0", x)))
+    x = torch.tanh(layer_norm(p, "output_layers.5", linear(p, "output_layers.4", x)))
+    return (x, inter) if return_intermediates else x

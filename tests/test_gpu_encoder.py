@@ -1,0 +1,110 @@
+"""DrQ-v2 visual encoder on the sm_100a path vs the reference goldens and the oracle.
+
+Tolerances: bf16x3 operands (fp32-grade) rel-L2 <= 1e-3 on the features; bf16 operands: stated
+bound 3e-2 (four conv layers, a 451,584-long reduction and three normalisations; measured values
+are printed by the tests)."""
+import os
+
+import pytest
+import torch
+
+from oracle import restatement as R
+from oracle.harness import perturb_generic
+from tests.util import gen, rel_l2
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = {"bf16x3": 1e-3, "bf16": 3e-2}
+
+
+def build(d, weights, precision):
+    from active_inference_diffusion_b200 import DrQV2Encoder
+    enc = DrQV2Encoder(tuple(d["obs_shape"]), feature_dim=d["feature_dim"], frame_stack=d["frame_stack"],
+                       num_filters=d["num_filters"], use_attention=d["use_attention"])
+    enc.load_state_dict(weights)
+    enc = enc.cuda().eval()
+    enc.precision = precision
+    return enc
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("name", ["encoder_small", "encoder_small_odd"])
+def test_encoder_vs_reference_golden(name, precision):
+    fx = torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
+    enc = build(fx["dims"], fx["weights"], precision)
+    for kind, x in fx["inputs"].items():
+        got = enc(x.cuda())
+        err = rel_l2(got, fx["outputs"][kind])
+        print(name, precision, kind, err)
+        assert err < TOL[precision], (kind, err)
+
+
+def oracle_on_gpu(weights, x):
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            return R.encoder_forward({k: v.cuda() for k, v in weights.items()}, x, return_intermediates=True)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_encoder_full_size_vs_oracle(precision):
+    """BASELINE cfg#5 shape: 3x84x84 frames, stack 3, feature_dim 128 (conv_out_dim 451,584, 117 M parameters)."""
+    from active_inference_diffusion_b200 import DrQV2Encoder
+    torch.manual_seed(2)
+    enc = DrQV2Encoder((3, 84, 84), feature_dim=128, frame_stack=3)
+    assert enc.conv_out_dim == 451584
+    enc.load_state_dict(perturb_generic(enc.state_dict(), 41, 0.02))
+    weights = {k: v.clone() for k, v in enc.state_dict().items()}
+    enc = enc.cuda().eval()
+    enc.precision = precision
+    x = torch.randint(0, 256, (3, 9, 84, 84), generator=gen(8), dtype=torch.uint8).cuda()
+    got = enc(x)
+    want, _ = oracle_on_gpu(weights, x.float() / 255.0)
+    err = rel_l2(got, want)
+    print("full size", precision, err)
+    assert err < TOL[precision], err
+    # rows are independent: a sub-batch reproduces its rows bit for bit
+    assert torch.equal(enc(x[1:2]), got[1:2])
+
+
+def test_encoder_chunked_batch_and_weight_updates():
+    """Batches larger than the internal image chunk (256) and the packed-weight cache invalidation."""
+    fx = torch.load(os.path.join(GOLD, "encoder_small.pt"), weights_only=False)
+    d = fx["dims"]
+    enc = build(d, fx["weights"], "bf16x3")
+    x = torch.rand(300, d["frame_stack"] * d["obs_shape"][0], *d["obs_shape"][1:], generator=gen(3))
+    with torch.no_grad():
+        want = R.encoder_forward(fx["weights"], x)
+    got = enc(x.cuda())
+    assert rel_l2(got, want) < 1e-3, rel_l2(got, want)
+    assert torch.equal(got[256:], enc(x[256:].cuda()))
+    with torch.no_grad():
+        enc.output_layers[4].bias.add_(0.25)
+    w2 = {k: v.detach().cpu().clone() for k, v in enc.state_dict().items()}
+    with torch.no_grad():
+        want2 = R.encoder_forward(w2, x[:4])
+    assert rel_l2(enc(x[:4].cuda()), want2) < 1e-3
+
+
+def test_encoder_input_conventions_and_errors():
+    fx = torch.load(os.path.join(GOLD, "encoder_small.pt"), weights_only=False)
+    d = fx["dims"]
+    enc = build(d, fx["weights"], "bf16")
+    c, h, w = d["obs_shape"]
+    one = torch.rand(d["frame_stack"] * c, h, w, generator=gen(1)).cuda()
+    assert enc(one).shape == (1, d["feature_dim"])                      # 3-D input gains a batch axis
+    with pytest.raises(ValueError):
+        enc(torch.rand(2, c + 1, h, w).cuda())
+    with pytest.raises(ValueError):
+        enc(torch.rand(h, w).cuda())
+    with pytest.raises(AssertionError):
+        enc(torch.rand(2, d["frame_stack"] + 1, c, h, w).cuda())
+    with pytest.raises(RuntimeError):
+        enc(torch.rand(2, d["frame_stack"] * c, h, w))                   # CPU tensor: no fallback
+    enc.train()
+    with pytest.raises(NotImplementedError):
+        enc(one)

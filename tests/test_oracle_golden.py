@@ -170,3 +170,32 @@ def test_belief_update_restatement_properties():
                                     min_variance=c["min_variance"])
     assert np.allclose(m2, mean) and np.allclose(S, S.T)
     assert np.allclose(P @ (S + max(c["min_variance"], 1e-8) * np.eye(L)), np.eye(L), atol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["encoder_small", "encoder_small_odd"])
+def test_encoder_forward_golden(name):
+    """DrQ-v2 encoder restatement vs the unmodified reference (uint8, 5-D float and single-frame
+    inputs; the second fixture has odd sizes and no attention)."""
+    fx = load(name)
+    d = fx["dims"]
+    for kind, x in fx["inputs"].items():
+        xin = R.encoder_canonical_input(x, d["obs_shape"][0], d["frame_stack"])
+        with torch.no_grad():
+            got = R.encoder_forward(fx["weights"], xin)
+        assert torch.allclose(got, fx["outputs"][kind], rtol=0, atol=2e-6), (kind, float((got - fx["outputs"][kind]).abs().max()))
+
+
+@pytest.mark.parametrize("name", ["encoder_small", "encoder_small_odd"])
+def test_encoder_mirror_seeded_init_matches_reference(name):
+    """The mirror's constructor spends the same draws in the same order as the reference's, so the
+    same seed gives the same state_dict (spectral-norm u/v after the dry-run power iteration included)."""
+    from active_inference_diffusion_b200 import DrQV2Encoder
+    fx = load(name)
+    d = fx["dims"]
+    torch.manual_seed(fx["seed"])
+    enc = DrQV2Encoder(tuple(d["obs_shape"]), feature_dim=d["feature_dim"], frame_stack=d["frame_stack"],
+                       num_filters=d["num_filters"], use_attention=d["use_attention"])
+    sd = enc.state_dict()
+    assert list(sd.keys()) == list(fx["init_state"].keys())
+    for k, v in fx["init_state"].items():
+        assert torch.equal(sd[k], v), k
