@@ -183,11 +183,13 @@ static int launch_gemm_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t 
   }
   const int a_bytes = RES ? ga.kb * TILE_BYTES : 0;
   const int slot = NW * TILE_BYTES;
-  int ring = (SMEM_LIMIT - 1024 - SMEM_CTRL - a_bytes) / slot;
+  const int tab_bytes = ga.conv.cin8 ? CONV_TAB_BYTES : 0;   // implicit-im2col address table after the ring
+  if (ga.kb * 8 * 8 > CONV_TAB_BYTES && tab_bytes) return fail("gemm: conv K too long for the address table");
+  int ring = (SMEM_LIMIT - 1024 - SMEM_CTRL - a_bytes - tab_bytes) / slot;
   if (ring > MAX_RING) ring = MAX_RING;
   if (ring < (RES ? 2 : G + 2)) return fail("gemm: not enough shared memory for the ring");
-  const size_t smem = 1024 + SMEM_CTRL + a_bytes + (size_t)ring * slot;
-  const int units = ga.row_tiles * (ga.n_tiles / (NW * G));
+  const size_t smem = 1024 + SMEM_CTRL + a_bytes + (size_t)ring * slot + tab_bytes;
+  const int units = (ga.splits > 1 ? ga.splits : 1) * ga.row_tiles * (ga.n_tiles / (NW * G));
   int grid = units < num_sms() ? units : num_sms();
   if (grid < 1) return 0;
   const bool prof = g_prof.on && g_prof.epi == EPI && g_prof.kb == ga.kb && g_prof.n_tiles == ga.n_tiles &&
@@ -225,10 +227,12 @@ static int launch_gemm2_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t
   const int a_bytes = RES ? ga.kb * TILE_BYTES : 0;
   const int slot = (RES ? 1 : 2) * TILE_BYTES;
   constexpr int stage_out = gemm2_stage_bytes(EPI);
-  int ring = (SMEM_LIMIT - 1024 - SMEM_CTRL - stage_out - a_bytes) / slot;
+  const int tab_bytes = ga.conv.cin8 ? CONV_TAB_BYTES : 0;
+  if (ga.kb * 8 * 8 > CONV_TAB_BYTES && tab_bytes) return fail("gemm2: conv K too long for the address table");
+  int ring = (SMEM_LIMIT - 1024 - SMEM_CTRL - stage_out - a_bytes - tab_bytes) / slot;
   if (ring > MAX_RING2) ring = MAX_RING2;
   if (ring < 2) return fail("gemm2: not enough shared memory for the ring");
-  const size_t smem = 1024 + SMEM_CTRL + stage_out + a_bytes + (size_t)ring * slot;
+  const size_t smem = 1024 + SMEM_CTRL + stage_out + a_bytes + (size_t)ring * slot + tab_bytes;
   const int units = ((ga.row_tiles + 1) / 2) * (ga.n_tiles / 2);
   const int max_pairs = num_sms() / 2;
   const int pairs = units < max_pairs ? units : max_pairs;
@@ -271,8 +275,10 @@ static int launch_gemm_shape(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t
 
 template <int EPI>
 static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs ea, cudaStream_t st,
-                       int* err_flag, int splits = 1) {
+                       int* err_flag, int splits = 1, const ConvA* conv = nullptr) {
   GemmArgs ga;
+  memset(&ga.conv, 0, sizeof(ga.conv));
+  if (conv) ga.conv = *conv;
   ga.A = A;
   ga.B = w.w;
   ga.row_tiles = row_tiles;
@@ -291,7 +297,7 @@ static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs e
   static thread_local unsigned flip = 0;
   ga.reverse = (dbg & 8) ? 0 : (int)(flip++ & 1);
   if (!ea.bias) ea.bias = w.b;
-  const bool res = ga.kb <= MAX_RES_KB;
+  const bool res = ga.kb <= MAX_RES_KB && !conv;   // the implicit-im2col producer streams A
   const bool wide = w.nw == 2;   // N=256 MMAs whenever the tile count allows (fixed at pack time)
   // A resident in shared memory (K <= 512) or streamed through the ring.  Streamed A: one N=256
   // unit per pass so TMEM holds two units and the epilogue of unit u overlaps the MMAs of unit u+1

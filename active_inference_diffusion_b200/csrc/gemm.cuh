@@ -47,7 +47,22 @@ enum EpiKind : int {
   EPI_SCORE = 3,  // clamp/scale score, optional reverse-diffusion step -> z (fp32 row-major + packed)
 };
 
+// Implicit im2col of a 3x3 / stride-1 / padding-1 convolution (encoder.inc): the A operand is the
+// "halo" activation [Cin/8 planes][guard + virtual rows + guard][8 bf16] and the K chunk (tap, 8
+// channels) of 128 consecutive output rows is one contiguous 2 KiB run of it, so the producer
+// fetches a k-block as eight 2 KiB bulk copies instead of one packed 16 KiB tile.  cin8 == 0: off.
+struct ConvA {
+  const uint8_t* hi;
+  const uint8_t* lo;        // low halves (bf16x3 operand split), regions [hi | hi | lo] along K
+  long long plane_bytes;    // bytes per 8-channel plane
+  int guard;                // zero guard rows in front of every plane (>= 128: also the zero K padding)
+  int cin8;                 // Cin / 8
+  int vw;                   // virtual row width (Wo + 2)
+  int kreg8;                // 16-byte chunks per region when split, else 0
+};
+
 struct GemmArgs {
+  ConvA conv;
   const uint8_t* A;  // packed
   const uint8_t* B;  // packed
   int row_tiles;
@@ -95,6 +110,41 @@ struct EpiArgs {
   float c_s1, c_ra, c_c1, c_c2, c_sigma;
   float* z_out;              // row-major fp32 (score or new z)
 };
+
+// The source address of K chunk g for row tile 0 depends only on g; it is tabulated in shared
+// memory once per CTA (the first version recomputed it with integer divisions in the single
+// producer thread, ~3000 cycles of dependent instructions per k-block: the implicit GEMMs ran 2.5x
+// slower than GEMMs on packed tiles).  CONV_TAB_BYTES of dynamic shared memory follow the ring.
+constexpr int CONV_TAB_BYTES = 16384;
+__device__ __forceinline__ void conv_fill_table(const ConvA& c, unsigned long long* tab, int chunks) {
+  for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
+    int g = i;
+    bool want_lo = false;
+    if (c.kreg8) {
+      const int region = g / c.kreg8;
+      g -= region * c.kreg8;
+      want_lo = region == 2;
+    }
+    // K padding: the zero guard rows of plane 0, flagged in bit 0 (does not move with the row tile)
+    unsigned long long entry = reinterpret_cast<unsigned long long>(c.hi) | 1ull;
+    if (g < 9 * c.cin8) {
+      const int tap = g / c.cin8, c8 = g - tap * c.cin8;
+      const long long row = (long long)c.guard + (tap / 3 - 1) * c.vw + (tap % 3 - 1);
+      entry = reinterpret_cast<unsigned long long>((want_lo ? c.lo : c.hi) + (long long)c8 * c.plane_bytes + row * 16);
+    }
+    tab[i] = entry;
+  }
+}
+__device__ __forceinline__ void conv_load_a(const ConvA& c, const unsigned long long* tab, uint32_t dst, int rt,
+                                            int kb, uint32_t bar, uint64_t policy) {
+  const unsigned long long row_off = (unsigned long long)rt * (TILE_M * 16);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const unsigned long long t = tab[kb * 8 + j];
+    const uint8_t* src = reinterpret_cast<const uint8_t*>((t & 1ull) ? t - 1ull : t + row_off);
+    bulk_g2s_hint(dst + j * (TILE_M * 16), src, TILE_M * 16, bar, policy);
+  }
+}
 
 // element offset of (row r, col c) inside an R-row x 64-col packed tile
 __device__ __forceinline__ int packed_off(int r, int c, int R = TILE_M) {
@@ -250,6 +300,9 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
   }
   // Programmatic dependent launch: the prologue above (barrier init, TMEM allocation) overlaps the
   // tail of the previous kernel of the chain; nothing below touches global memory before the wait.
+  unsigned long long* conv_tab =
+      reinterpret_cast<unsigned long long*>(smem + SMEM_CTRL + (RES ? ga.kb * TILE_BYTES : 0) + ring_stages * SLOT_BYTES);
+  if (ga.conv.cin8) conv_fill_table(ga.conv, conv_tab, ga.kb * 8);
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
@@ -286,8 +339,11 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
             const uint32_t fb = smem_u32(&ctrl->ring_full[stage]);
             mbar_wait(smem_u32(&ctrl->ring_empty[stage]), phase ^ 1, ga.err, 2);
             mbar_arrive_expect_tx(fb, TILE_BYTES);
-            bulk_g2s_hint(ring_smem + stage * SLOT_BYTES, ga.A + (a_row + kb) * TILE_BYTES, TILE_BYTES, fb,
-                          (ga.debug & 8) ? once : keep);
+            if (ga.conv.cin8)
+              conv_load_a(ga.conv, conv_tab, ring_smem + stage * SLOT_BYTES, rt, kb, fb, keep);
+            else
+              bulk_g2s_hint(ring_smem + stage * SLOT_BYTES, ga.A + (a_row + kb) * TILE_BYTES, TILE_BYTES, fb,
+                            (ga.debug & 8) ? once : keep);
             if (++stage == ring_stages) { stage = 0; phase ^= 1; }
           }
 #pragma unroll

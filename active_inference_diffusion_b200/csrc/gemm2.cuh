@@ -165,6 +165,9 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
     tmem_alloc2(smem_u32(&ctrl->tmem_base), 512);
     tmem_relinquish2();
   }
+  unsigned long long* conv_tab = reinterpret_cast<unsigned long long*>(
+      smem + SMEM_CTRL + STAGE_OUT + (RES ? ga.kb * TILE_BYTES : 0) + ring_stages * STAGE_BYTES2);
+  if (ga.conv.cin8) conv_fill_table(ga.conv, conv_tab, ga.kb * 8);
   pdl_launch_dependents();                                    // see gemm.cuh: prologue overlaps the previous kernel's tail
   tc_fence_before();
   cluster_sync_all();                                         // barriers of BOTH CTAs are live
@@ -184,6 +187,7 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       int stage = 0;
       uint32_t phase = 0, a_par = 0;
       int prev_rp = -1;
+      const uint64_t conv_policy = policy_evict_last();   // halo rows are re-read by the other eight taps
       for (int u = u_begin; u < u_end; ++u) {
         int rp, ng;
         unit_coords(u, rp, ng);
@@ -206,7 +210,10 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
             mbar_arrive_expect_tx(fb, STAGE_BYTES2);
             uint32_t dst = ring_smem + stage * STAGE_BYTES2;
             if (!RES) {
-              bulk_g2s(dst, ga.A + ((size_t)rt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
+              if (ga.conv.cin8)
+                conv_load_a(ga.conv, conv_tab, dst, rt, kb, fb, conv_policy);
+              else
+                bulk_g2s(dst, ga.A + ((size_t)rt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
               dst += TILE_BYTES;
             }
             bulk_g2s(dst, ga.B + ((size_t)nt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);

@@ -108,3 +108,35 @@ def test_encoder_input_conventions_and_errors():
     enc.train()
     with pytest.raises(NotImplementedError):
         enc(one)
+
+
+@pytest.mark.parametrize("env", [{"AID_ENC_IMPLICIT": "0"}, {"AID_ENC_CHUNK": "2"}])
+def test_encoder_alternative_paths_subprocess(env):
+    """Knobs read once per process: AID_ENC_IMPLICIT=0 = explicit im2col tiles instead of the
+    producer-side halo gather (the two must agree bit for bit: same operands, same MMA order);
+    AID_ENC_CHUNK=2 = many small image chunks (ragged last chunk)."""
+    import subprocess, sys
+    code = ("import os, torch\n"
+            "from oracle import restatement as R\n"
+            "from tests.util import gen, rel_l2\n"
+            "from tests.test_gpu_encoder import build, GOLD\n"
+            "for name in ('encoder_small', 'encoder_small_odd'):\n"
+            "    fx = torch.load(os.path.join(GOLD, name + '.pt'), weights_only=False)\n"
+            "    for prec in ('bf16x3', 'bf16'):\n"
+            "        enc = build(fx['dims'], fx['weights'], prec)\n"
+            "        got = enc(fx['inputs']['u8'].cuda())\n"
+            "        e = rel_l2(got, fx['outputs']['u8']); print(name, prec, e)\n"
+            "        assert e < (1e-3 if prec == 'bf16x3' else 3e-2), e\n"
+            "        torch.save(got.cpu(), os.environ['AID_TEST_OUT'] + name + prec + '.pt')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        outs = {}
+        for tag, e in (("alt", env), ("default", {})):
+            out = subprocess.run([sys.executable, "-c", code],
+                                 env=dict(os.environ, AID_TEST_OUT=os.path.join(tmp, tag), **e), cwd=root,
+                                 capture_output=True, text=True, timeout=600)
+            assert out.returncode == 0, out.stderr[-2000:]
+            outs[tag] = {f: torch.load(os.path.join(tmp, f)) for f in sorted(os.listdir(tmp)) if f.startswith(tag)}
+        for (ka, va), (kd, vd) in zip(sorted(outs["alt"].items()), sorted(outs["default"].items())):
+            assert torch.equal(va, vd), (ka, kd, float((va - vd).abs().max()))
