@@ -60,6 +60,17 @@ class CandidateScorer(nn.Module):
         return efe, first_action, latent
 
     @torch.no_grad()
+    def forward_pixels(self, encoder: nn.Module, pixels: torch.Tensor, **kw
+                       ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Pixel observations (BASELINE cfg#5): `DrQV2Encoder` features are the score net's
+        observation, as in `DiffusionPixelAgent.act` (agents/pixel_agent.py:193-205: encode ->
+        belief update -> EFE); requires observation_dim == encoder.feature_dim."""
+        features = encoder(pixels)
+        if features.shape[1] != self.observation_dim:
+            raise ValueError(f"encoder feature_dim {features.shape[1]} != observation_dim {self.observation_dim}")
+        return self.forward(features, **kw)
+
+    @torch.no_grad()
     def collect_actions(self, observation_host: torch.Tensor, max_diffusion_steps: int = 20, *,
                         deterministic: bool = False, z_init: Optional[torch.Tensor] = None,
                         noise: Optional[torch.Tensor] = None, policy_noise: Optional[torch.Tensor] = None

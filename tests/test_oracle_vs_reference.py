@@ -59,3 +59,27 @@ def test_reverse_diffusion_with_recorded_draws(ref, sched, T):
     assert len(got) == len(traj)
     for a, b in zip(got, traj):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("shape,stack,F,nf,att,sn", [((3, 16, 20), 2, 12, 8, True, True), ((1, 9, 9), 1, 10, 16, False, False)])
+def test_encoder_restatement_and_mirror_init(shape, stack, F, nf, att, sn):
+    """DrQV2Encoder (encoder/visual_encoders.py): fresh seed, eval forward of the restatement, and the
+    mirror's constructor against the reference's (same seed -> same state_dict)."""
+    import_reference()
+    from active_inference_diffusion.encoder.visual_encoders import DrQV2Encoder as RefEncoder
+    from active_inference_diffusion_b200 import DrQV2Encoder
+    torch.manual_seed(13)
+    ref = RefEncoder(shape, feature_dim=F, frame_stack=stack, num_filters=nf, use_attention=att, use_spectral_norm=sn)
+    torch.manual_seed(13)
+    mine = DrQV2Encoder(shape, feature_dim=F, frame_stack=stack, num_filters=nf, use_attention=att, use_spectral_norm=sn)
+    rsd, msd = ref.state_dict(), mine.state_dict()
+    assert list(rsd.keys()) == list(msd.keys())
+    for k in rsd:
+        assert torch.equal(rsd[k], msd[k]), k
+    assert mine.conv_out_dim == ref.conv_out_dim
+    ref.eval()
+    x = torch.randint(0, 256, (4, stack * shape[0], shape[1], shape[2]), dtype=torch.uint8)
+    with torch.no_grad():
+        want = ref(x)
+        got = R.encoder_forward({k: v.clone() for k, v in rsd.items()}, R.encoder_canonical_input(x, shape[0], stack))
+    assert torch.allclose(got, want, rtol=0, atol=2e-6)
