@@ -121,6 +121,9 @@ def _declare_train(l: ctypes.CDLL) -> None:
 def _declare_misc(l: ctypes.CDLL) -> None:
     l.aid_time_importance_update.restype = c_int32
     l.aid_time_importance_update.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]
+    l.aid_lambda_returns.restype = c_int32
+    l.aid_lambda_returns.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, ctypes.c_double, ctypes.c_double,
+                                     c_int32, c_int32, c_void_p, c_void_p]
 
 
 def _declare_encoder(l: ctypes.CDLL) -> None:
@@ -262,6 +265,21 @@ def time_importance_update(t: torch.Tensor, loss: torch.Tensor, weights: torch.T
     check(lib().aid_time_importance_update(ptr(t), ptr(loss), t.numel(), ptr(weights), weights.numel(), ptr(bins),
                                            stream_ptr(dev)), "aid_time_importance_update")
     return bins
+
+
+def lambda_returns(rewards: torch.Tensor, next_values: torch.Tensor, dones: torch.Tensor, discount_factor: float,
+                   lambda_: float = 0.95, n_steps: int = 5, exclude_immediate_rewards: bool = False) -> torch.Tensor:
+    """lambda-returns over the batch axis (aid_lambda_returns); all inputs [B] on the device."""
+    dev = require_cuda(rewards, next_values, dones)
+    r, nv = f32c(rewards.detach().reshape(-1)), f32c(next_values.detach().reshape(-1))
+    d = (dones.reshape(-1) != 0).to(torch.uint8).contiguous()
+    if not (r.numel() == nv.numel() == d.numel()):
+        raise ValueError("rewards, next_values and dones must have the same length")
+    out = torch.empty_like(r)
+    check(lib().aid_lambda_returns(ptr(r), ptr(nv), ptr(d), r.numel(), float(discount_factor), float(lambda_),
+                                   int(n_steps), int(bool(exclude_immediate_rewards)), ptr(out), stream_ptr(dev)),
+          "aid_lambda_returns")
+    return out.reshape(rewards.shape)
 
 
 def profile_select(epi: int, k: int = 0, n: int = 0) -> None:

@@ -381,6 +381,15 @@ class DiffusionActiveInference(nn.Module):
                 "mean_time", "loss_weight_mean"]
         return -elbo, {k: float(v) for k, v in zip(keys, vals)}
 
+    def compute_lambda_returns(self, rewards: torch.Tensor, values: torch.Tensor, next_values: torch.Tensor,
+                               dones: torch.Tensor, lambda_: float = 0.95, n_steps: int = 5,
+                               exclude_immediate_rewards: bool = False) -> torch.Tensor:
+        """Reference :638-707 (value targets of `train_step`, agents/state_agent.py:198-205): an
+        O(B n^2) Python loop over 0-dim tensors there, one kernel here with the same fp32 operation
+        order.  `values` is accepted and ignored, as in the reference."""
+        return _lib.lambda_returns(rewards, next_values, dones, self.config.discount_factor, lambda_, n_steps,
+                                   exclude_immediate_rewards)
+
     def _compute_gradient_penalty(self, noisy_latents, t, observations) -> torch.Tensor:
         x = noisy_latents.detach().requires_grad_(True)
         s = autograd_path.score_forward(self.latent_score_network, x, t, observations)

@@ -210,6 +210,17 @@ int32_t aid_fp_belief_update(const double* mean, const double* variance, const d
 int32_t aid_time_importance_update(const float* t, const float* loss, int32_t n, float* weights,
                                    int32_t n_bins, int64_t* bins_out, void* stream);
 
+/* ---- compute_lambda_returns — core/active_inference.py:638-707 -----------------
+ * Dreamer-style lambda-returns over the batch axis exactly as the reference's Python loop computes
+ * them (fp32, same operation order; bit-identical to it on CPU tensors): out[i] mixes the n-step
+ * returns n = 1..min(n_steps, batch-1-i) with weights (1-lambda)lambda^(n-1), the last one taking
+ * lambda^(N-1), normalised by their sum + 1e-8; indices with no n-step return get the one-step TD
+ * target.  rewards, next_values, out: [batch] fp32; dones: [batch] uint8 (non-zero = terminal).
+ * The reference's `values` argument is unused by its body (:641) and has no counterpart here. */
+int32_t aid_lambda_returns(const float* rewards, const float* next_values, const uint8_t* dones,
+                           int32_t batch, double discount_factor, double lambda, int32_t n_steps,
+                           int32_t exclude_immediate_rewards, float* out, void* stream);
+
 /* ---- DrQV2Encoder.forward — encoder/visual_encoders.py:13-189 (+ SpatialAttention :192-224) ---
  * SURVEY.md §8 f-1.  Eval-mode forward: 3x3 convs (first stride 2) with spectral-norm scaling
  * W/sigma, sigma = u^T W v from the stored buffers (no power iteration), GroupNorm(min(32,C/4)) +

@@ -178,6 +178,26 @@ def gen_encoder(name, obs_shape, frame_stack, feature_dim, num_filters, B, use_a
     print(name, "features max", float(outs["u8"].abs().max()), "conv_out_dim", enc.conv_out_dim)
 
 
+def gen_lambda_returns(name):
+    """compute_lambda_returns (core/active_inference.py:638-707) called unbound on a stub carrying
+    config.discount_factor: the method touches nothing else of the object."""
+    from active_inference_diffusion.core.active_inference import DiffusionActiveInference
+    stub = types.SimpleNamespace(config=types.SimpleNamespace(discount_factor=0.99))
+    g = torch.Generator().manual_seed(5)
+    cases = []
+    for B in (1, 2, 3, 7, 40):
+        for n_steps in (0, 1, 5, 8):
+            for excl in (False, True):
+                r, nv = torch.randn(B, generator=g), torch.randn(B, generator=g)
+                d = torch.rand(B, generator=g) < 0.2
+                out = DiffusionActiveInference.compute_lambda_returns(stub, r, None, nv, d, lambda_=0.95, n_steps=n_steps,
+                                                                      exclude_immediate_rewards=excl)
+                cases.append(dict(rewards=r, next_values=nv, dones=d, gamma=0.99, lam=0.95, n_steps=n_steps,
+                                  exclude=excl, out=out))
+    torch.save({"cases": cases}, os.path.join(OUT, f"{name}.pt"))
+    print(name, len(cases), "cases")
+
+
 def main():
     import_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -186,6 +206,7 @@ def main():
     gen_score_and_sampler("score_default_dims", 128, 17, 512, 6, 50, 8, "cosine", False)
     gen_active_inference("active_inference_small", 32, 6, 64, 6, 9)
     gen_misc("free_energy_belief")
+    gen_lambda_returns("lambda_returns")
     gen_encoder("encoder_small", (3, 12, 12), 3, 16, 8, 5)
     gen_encoder("encoder_small_odd", (1, 11, 14), 2, 8, 8, 3, use_attention=False)
 

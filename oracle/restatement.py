@@ -660,3 +660,46 @@ def encoder_forward(p: Params, x: torch.Tensor, return_intermediates: bool = Fal
     x = F.mish(layer_norm(p, "output_layers.1", linear(p, "output_layers.0", x)))
     x = torch.tanh(layer_norm(p, "output_layers.5", linear(p, "output_layers.4", x)))
     return (x, inter) if return_intermediates else x
+
+
+# --------------------------------------------------------------------------
+# lambda-returns — core/active_inference.py:638-707
+# --------------------------------------------------------------------------
+
+def lambda_returns(rewards: torch.Tensor, next_values: torch.Tensor, dones: torch.Tensor, gamma: float,
+                   lam: float = 0.95, n_steps: int = 5, exclude_immediate_rewards: bool = False) -> torch.Tensor:
+    """Dreamer-style lambda-returns along the batch axis, restated with the reference's arithmetic
+    (0-dim fp32 tensor ops in the same order, Python-float weights) so the result is bit-identical:
+    for every index the n-step returns n = 1..min(n_steps, B-1-i) (discounted reward prefix, the
+    discount killed by a terminal flag, bootstrap from next_values[i+n] unless step i+n-1 was
+    terminal) are mixed with (1-lam) lam^(n-1), the last taking lam^(N-1), and normalised by the
+    weight sum + 1e-8 (:686-700); without any n-step return the one-step TD target is used (:701-705)."""
+    B = rewards.shape[0]
+    out = torch.zeros_like(rewards)
+    alive = 1 - dones.float()
+    for i in range(B):
+        N = min(n_steps, B - 1 - i)
+        if N <= 0:
+            boot = gamma * alive[i] * next_values[i]
+            out[i] = boot if exclude_immediate_rewards else rewards[i] + boot
+            continue
+        prefix, disc, rets = 0, 1.0, []
+        for n in range(1, N + 1):
+            k = n - 1
+            if not (exclude_immediate_rewards and k == 0):
+                prefix = prefix + disc * rewards[i + k]
+            disc = disc * (gamma * alive[i + k])
+            ret = prefix
+            if i + n < B and not bool(dones[i + n - 1]):
+                ret = ret + disc * next_values[i + n]
+            rets.append(ret)
+        total, wsum = 0, 0
+        for j, ret in enumerate(rets[:-1]):
+            wj = (1 - lam) * (lam ** j)
+            total = total + wj * ret
+            wsum += wj
+        w_last = lam ** (len(rets) - 1)
+        total = total + w_last * rets[-1]
+        wsum += w_last
+        out[i] = total / (wsum + 1e-8)
+    return out

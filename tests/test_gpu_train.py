@@ -110,3 +110,27 @@ def test_time_importance_update_is_bit_exact(n):
     bins = _lib.time_importance_update(t.cuda(), loss.cuda(), w, want_bins=True)
     assert torch.equal(w.cpu(), want)
     assert torch.equal(bins.cpu(), R.time_importance_bins(t))
+
+
+def test_lambda_returns_bit_exact_vs_golden_and_oracle():
+    """aid_lambda_returns: bit-identical to the reference's Python loop on the golden
+    cases and to the oracle on a 4,099-long batch with long n_steps."""
+    import os
+    from active_inference_diffusion_b200 import _lib
+    from oracle import restatement as R
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lambda_returns.pt"),
+                    weights_only=False)
+    for c in fx["cases"]:
+        got = _lib.lambda_returns(c["rewards"].cuda(), c["next_values"].cuda(), c["dones"].cuda(), c["gamma"], c["lam"],
+                                  c["n_steps"], c["exclude"])
+        assert torch.equal(got.cpu(), c["out"]), (c["n_steps"], c["exclude"])
+    g = torch.Generator().manual_seed(1)
+    B = 4099
+    r, nv = torch.randn(B, generator=g), torch.randn(B, generator=g)
+    for dones in (torch.rand(B, generator=g) < 0.1, (torch.rand(B, generator=g) < 0.3).float()):
+        for n_steps, excl in ((5, False), (17, True), (64, False)):
+            want = R.lambda_returns(r, nv, dones, 0.97, 0.9, n_steps, excl)
+            got = _lib.lambda_returns(r.cuda(), nv.cuda(), dones.cuda(), 0.97, 0.9, n_steps, excl)
+            assert torch.equal(got.cpu(), want), (n_steps, excl, float((got.cpu() - want).abs().max()))
+    with pytest.raises(RuntimeError):
+        _lib.lambda_returns(r.cuda(), nv.cuda(), dones.cuda(), 0.97, 0.9, 65, False)

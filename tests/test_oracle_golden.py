@@ -199,3 +199,13 @@ def test_encoder_mirror_seeded_init_matches_reference(name):
     assert list(sd.keys()) == list(fx["init_state"].keys())
     for k, v in fx["init_state"].items():
         assert torch.equal(sd[k], v), k
+
+
+def test_lambda_returns_golden_bit_exact():
+    """compute_lambda_returns restatement vs the unmodified reference (all batch sizes incl. 1 and 2,
+    n_steps 0/1/5/8, both exclude_immediate_rewards settings, random terminal flags)."""
+    fx = load("lambda_returns")
+    assert len(fx["cases"]) == 40
+    for c in fx["cases"]:
+        got = R.lambda_returns(c["rewards"], c["next_values"], c["dones"], c["gamma"], c["lam"], c["n_steps"], c["exclude"])
+        assert torch.equal(got, c["out"]), (c["n_steps"], c["exclude"], got, c["out"])
