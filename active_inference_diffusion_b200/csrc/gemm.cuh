@@ -135,6 +135,14 @@ __device__ __forceinline__ void conv_fill_table(const ConvA& c, unsigned long lo
     tab[i] = entry;
   }
 }
+// one 2 KiB chunk (j = 0..7) of k-block kb: the warp-wide producers give one chunk to each of 8 lanes
+__device__ __forceinline__ void conv_load_chunk(const unsigned long long* tab, uint32_t dst, int rt, int kb, int j,
+                                                uint32_t bar, uint64_t policy) {
+  const unsigned long long t = tab[kb * 8 + j];
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(
+      (t & 1ull) ? t - 1ull : t + (unsigned long long)rt * (TILE_M * 16));
+  bulk_g2s_hint(dst + j * (TILE_M * 16), src, TILE_M * 16, bar, policy);
+}
 __device__ __forceinline__ void conv_load_a(const ConvA& c, const unsigned long long* tab, uint32_t dst, int rt,
                                             int kb, uint32_t bar, uint64_t policy) {
   const unsigned long long row_off = (unsigned long long)rt * (TILE_M * 16);
@@ -312,7 +320,39 @@ gemm_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
 
   if (warp == 0) {
     // ===================== producer =====================
-    if (lane == 0) {
+    if (!RES && ga.conv.cin8) {
+      // Implicit-im2col mode, warp-wide: lane 0 owns the barriers, lanes 0-7 each issue one 2 KiB
+      // chunk of the A k-block, lane 8 the weight tile.  (One thread issuing all nine copies of a
+      // k-block was the bottleneck: 506 vs 334 us for conv4 against the same GEMM on packed tiles.)
+      const uint64_t keep = policy_evict_last();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = u_begin; u < u_end; ++u) {
+        const int ue = unit_at(u);
+        const int rt = ue / groups, ng = ue % groups;
+        for (int kb = 0; kb < ga.kb; ++kb) {
+          uint32_t fb = smem_u32(&ctrl->ring_full[stage]);
+          if (lane == 0) {
+            mbar_wait(smem_u32(&ctrl->ring_empty[stage]), phase ^ 1, ga.err, 2);
+            mbar_arrive_expect_tx(fb, TILE_BYTES);
+          }
+          __syncwarp();
+          if (lane < 8) conv_load_chunk(conv_tab, ring_smem + stage * SLOT_BYTES, rt, kb, lane, fb, keep);
+          if (++stage == ring_stages) { stage = 0; phase ^= 1; }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            fb = smem_u32(&ctrl->ring_full[stage]);
+            if (lane == 8) {
+              mbar_wait(smem_u32(&ctrl->ring_empty[stage]), phase ^ 1, ga.err, 3);
+              mbar_arrive_expect_tx(fb, SLOT_BYTES);
+              bulk_g2s_hint(ring_smem + stage * SLOT_BYTES,
+                            ga.B + ((size_t)(ng * G + g) * ga.kb_stride + kb) * SLOT_BYTES, SLOT_BYTES, fb, keep);
+            }
+            if (++stage == ring_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (lane == 0) {
       // L2 policy: weight tiles are read by every CTA and a streamed A row tile is read again by
       // the next unit of the same CTA -> keep (evict_last); a resident A tile is read once ->
       // evict_first (ncu showed mlp.2 re-reading its 268 MB A operand from DRAM on the second pass).

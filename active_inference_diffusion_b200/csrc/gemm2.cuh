@@ -183,7 +183,30 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
 
   if (warp == 0) {
     // ===================== producer (both CTAs) =====================
-    if (lane == 0) {
+    if (!RES && ga.conv.cin8) {
+      // implicit-im2col mode, warp-wide (see gemm.cuh): lanes 0-7 one A chunk each, lane 8 the weights
+      const uint64_t conv_policy = policy_evict_last();   // halo rows are re-read by the other eight taps
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = u_begin; u < u_end; ++u) {
+        int rp, ng;
+        unit_coords(u, rp, ng);
+        const int rt = min(2 * rp + (int)rank, ga.row_tiles - 1);
+        const int nt = ng * TU + (int)rank;
+        for (int kb = 0; kb < ga.kb; ++kb) {
+          const uint32_t fb = smem_u32(&ctrl->ring_full[stage]);
+          if (lane == 0) {
+            mbar_wait(smem_u32(&ctrl->ring_empty[stage]), phase ^ 1, ga.err, 2);
+            mbar_arrive_expect_tx(fb, STAGE_BYTES2);
+          }
+          __syncwarp();
+          const uint32_t dst = ring_smem + stage * STAGE_BYTES2;
+          if (lane < 8) conv_load_chunk(conv_tab, dst, rt, kb, lane, fb, conv_policy);
+          else if (lane == 8) bulk_g2s(dst + TILE_BYTES, ga.B + ((size_t)nt * ga.kb + kb) * TILE_BYTES, TILE_BYTES, fb);
+          if (++stage == ring_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, a_par = 0;
       int prev_rp = -1;

@@ -72,16 +72,16 @@ def test_encoder_full_size_vs_oracle(precision):
 
 
 def test_encoder_chunked_batch_and_weight_updates():
-    """Batches larger than the internal image chunk (256) and the packed-weight cache invalidation."""
+    """Batches larger than the internal image chunk (512) and the packed-weight cache invalidation."""
     fx = torch.load(os.path.join(GOLD, "encoder_small.pt"), weights_only=False)
     d = fx["dims"]
     enc = build(d, fx["weights"], "bf16x3")
-    x = torch.rand(300, d["frame_stack"] * d["obs_shape"][0], *d["obs_shape"][1:], generator=gen(3))
+    x = torch.rand(600, d["frame_stack"] * d["obs_shape"][0], *d["obs_shape"][1:], generator=gen(3))
     with torch.no_grad():
         want = R.encoder_forward(fx["weights"], x)
     got = enc(x.cuda())
     assert rel_l2(got, want) < 1e-3, rel_l2(got, want)
-    assert torch.equal(got[256:], enc(x[256:].cuda()))
+    assert torch.equal(got[512:], enc(x[512:].cuda()))
     with torch.no_grad():
         enc.output_layers[4].bias.add_(0.25)
     w2 = {k: v.detach().cpu().clone() for k, v in enc.state_dict().items()}
