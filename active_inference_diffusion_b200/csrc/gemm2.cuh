@@ -141,8 +141,15 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
   const int groups = ga.n_tiles / TU;                         // units per row-tile pair
   const int rps = (ga.row_tiles + 1) >> 1;
   const int num_units = rps * groups;
-  const int u_begin = (int)((long long)pair * num_units / num_pairs);
-  const int u_end = (int)((long long)(pair + 1) * num_units / num_pairs);
+  // Resident A: a contiguous range of units per pair, so the resident row tiles serve all their
+  // column groups.  Streamed A: units are dealt round-robin, so the column groups of one row pair run
+  // at the same time on neighbouring pairs and the second read of the A tiles hits L2 (with contiguous
+  // ranges ncu showed mlp.2 reading 620 MB from DRAM for 404 MB of operands: the pair came back to
+  // the same 1 MB of A ~35 us later, after ~200 MB of other traffic had gone through the 126 MB L2).
+  const int u_lo = (int)((long long)pair * num_units / num_pairs);
+  const int u_hi = (int)((long long)(pair + 1) * num_units / num_pairs);
+  const int u_begin = 0;
+  const int u_end = RES ? u_hi - u_lo : (num_units - pair + num_pairs - 1) / num_pairs;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_RING2; ++i) {
@@ -175,7 +182,8 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
   const uint32_t tmem_base = ctrl->tmem_base;
   pdl_wait();                                                 // nothing above touched global memory
 
-  auto unit_coords = [&](int u, int& rp, int& ng) {
+  auto unit_coords = [&](int i, int& rp, int& ng) {   // i-th unit of this pair
+    const int u = RES ? u_lo + i : pair + i * num_pairs;
     const int ue = ga.reverse ? num_units - 1 - u : u;
     rp = ue / groups;
     ng = ue % groups;
