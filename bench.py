@@ -276,11 +276,11 @@ def run_ours(args):
                     "h2d_bytes_per_step": CANDIDATES * O * 4 * world, "d2h_bytes_per_step": CANDIDATES * (1 + A) * 4 * world},
             "gpu_launches": int(launches),
             "roofline": {
-                "bound": "tensor", "kernel": "gemm_kernel<EPI_PACK,NW=2,G=1,resident A,GELU> (mlp.0: [65536x512]x[512x2048] + bias + GELU -> packed bf16; largest share of the step's FLOPs)",
+                "bound": "tensor", "kernel": "gemm2_kernel<EPI_PACK,resident A,GELU> (CTA-pair tcgen05 kernel; mlp.0: [65536x512]x[512x2048] + bias + GELU -> packed bf16; largest share of the step's FLOPs)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); burst figure {peaks['burst']}",
                 "launches_timed": k_n, "avg_launch_ms": per_launch_ms, "flops_per_launch": fc1_flops,
-                "traffic": 295.1e6, "traffic_note": "dram bytes read+written per launch (86.0 + 209.1 MB) from profiles/r1_ncu_full_gemm_kernels_v3.csv; algorithmic: 67 MB packed A in + 268 MB packed activations out",
+                "traffic": 295.8e6, "traffic_note": "dram bytes read+written per launch (86.0 + 209.7 MB) from profiles/r1_ncu_full_gemm_kernels_v5_pairs.csv (ncu --set full); algorithmic: 67 MB packed A in + 268 MB packed activations out",
                 "whole_step_tflops": step_tflops, "whole_step_frac_of_peak": step_tflops / peak},
             "cpu_baseline": cb,
         }
