@@ -145,10 +145,57 @@ def time_cpu(steps: int, warmup: int):
     return CPU_SAMPLE / dt, dt, torch.get_num_threads()
 
 
+def run_reference_same_box(args):
+    """--impl reference --ref-device cuda: the same oracle port (= the reference's eager PyTorch
+    fp32 algorithm, TF32 off as in the reference's defaults) on this box's GPU instead of its host
+    cores.  Not the driver's reference arm (that one is the CPU run below): it is the 'same box'
+    bar of SURVEY.md §8(d), quoted in DESIGN.md."""
+    import torch
+    from oracle import restatement as R
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    params, heads, sched = cpu_models()
+    to = lambda d: {k: v.to(dev) for k, v in d.items()}
+    params, heads, sched = to(params), {k: to(v) for k, v in heads.items()}, to(sched)
+    B = args.ref_candidates
+    obs = build_inputs(1)[:B].to(dev)
+    cfg = dict(epistemic_weight=0.1, pragmatic_weight=1.0, consistency_weight=0.1, discount_factor=0.99,
+               preference_temperature=1.0)
+
+    def step():
+        with torch.no_grad():
+            zT = torch.randn(B, L, device=dev)
+            noise = [torch.randn(B, L, device=dev) for _ in range(T - 1)]
+            latent = R.generate_latent_trajectory(params, sched, zT, obs, noise)[-1]
+            nz = [dict(policy=torch.randn(B, A, device=dev), reparam=torch.randn(B, L, device=dev))
+                  for _ in range(K_TRAJ * HORIZON)]
+            return R.expected_free_energy(heads, cfg, latent, HORIZON, K_TRAJ, nz)[0]
+
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    print(json.dumps({"impl": "reference", "device": "cuda (eager PyTorch fp32, TF32 off)", "metric": METRIC,
+                      "value": B / ms * 1e3, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup,
+                      "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"{B} candidates per step, T={T} cosine reverse diffusion + horizon-{HORIZON} EFE",
+                                 "latent_dim": L, "hidden_dim": H, "num_blocks": NB}}))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.ref_device == "cuda":
+        return run_reference_same_box(args)
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
     value, dt, cores = time_cpu(steps, warmup)
     cb = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
@@ -296,6 +343,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="with --impl reference: cuda = the oracle port as eager PyTorch fp32 on this box's GPU")
+    ap.add_argument("--ref-candidates", type=int, default=CANDIDATES)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

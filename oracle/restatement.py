@@ -48,7 +48,7 @@ def sinusoidal_embedding(time: torch.Tensor, dim: int, freq_scale: torch.Tensor)
     """models/score_networks.py:282-291 — [sin | cos], freq_i = exp(-i ln(1e4)/(half-1)) * freq_scale."""
     half = dim // 2
     k = math.log(10000) / (half - 1)
-    freqs = torch.exp(torch.arange(half) * -k) * freq_scale
+    freqs = torch.exp(torch.arange(half, device=time.device) * -k) * freq_scale
     arg = time[:, None] * freqs[None, :]
     return torch.cat((arg.sin(), arg.cos()), dim=-1)
 
@@ -121,7 +121,7 @@ def score_conditioning(p: Params, time: torch.Tensor, obs: Optional[torch.Tensor
     if obs is not None:
         o_emb = obs_encoder(p, obs)
     else:
-        o_emb = torch.zeros(batch, p["obs_encoder.8.weight"].shape[0])
+        o_emb = torch.zeros(batch, p["obs_encoder.8.weight"].shape[0], device=p["obs_encoder.8.weight"].device)
     return t_emb + o_emb, time_weight
 
 
@@ -216,7 +216,7 @@ def generate_latent_trajectory(p: Params, sched: Dict[str, torch.Tensor], z_T: t
     traj = [z]
     draw = 0
     for t in reversed(range(T)):
-        tb = torch.full((z.shape[0],), float(t))
+        tb = torch.full((z.shape[0],), float(t), device=z.device)
         s = score_forward(p, z, tb, obs)
         eps = None
         if not deterministic and t != 0:
@@ -239,7 +239,7 @@ def collector_sample(p: Params, sched: Dict[str, torch.Tensor], z_init: torch.Te
     z = z_init
     draw = 0
     for step in reversed(range(num_steps)):
-        tc = torch.full((z.shape[0],), step / max_index if max_index > 0 else 0.0)
+        tc = torch.full((z.shape[0],), step / max_index if max_index > 0 else 0.0, device=z.device)
         s = score_forward(p, z, tc, obs)
         eps = None
         if step != 0:
@@ -419,12 +419,12 @@ def expected_free_energy(nets: Dict[str, Params], cfg: Dict[str, float], latent:
     Returns (efe[B], info dict of last-step means, first_action[B,A] of trajectory 0).
     """
     B = latent.shape[0]
-    total = torch.zeros(B)
+    total = torch.zeros(B, device=latent.device)
     epi_l, prag_l, cons_l = [], [], []
     first_action = None
     for k in range(num_trajectories):
         cur = latent.clone()
-        traj = torch.zeros(B)
+        traj = torch.zeros(B, device=latent.device)
         for t in range(horizon):
             nz = noise[k * horizon + t]
             action, _, _, std = policy_forward(nets["policy"], cur, nz["policy"])
@@ -434,14 +434,14 @@ def expected_free_energy(nets: Dict[str, Params], cfg: Dict[str, float], latent:
             nxt = mean + nz["reparam"] * torch.exp(0.5 * logvar)
             r_mean, _ = reward_head(nets["reward"], nxt)
             prag = cfg["pragmatic_weight"] * (r_mean / cfg["preference_temperature"])
-            prag = prag + value_forward(nets["value"], nxt, torch.full((B,), float(t))).squeeze(-1)
+            prag = prag + value_forward(nets["value"], nxt, torch.full((B,), float(t), device=latent.device)).squeeze(-1)
             cons = -normal_entropy(std).sum(-1)
             if epistemic == "mine":
                 epi, _, _, _, running_mean = epistemic_value(
                     nets["epistemic"], nets["decoder"], mean, logvar,
                     nz["z"], nz["dir"], nz["perm"], running_mean)
             else:
-                epi = torch.zeros(B)
+                epi = torch.zeros(B, device=latent.device)
             step = (cfg["epistemic_weight"] * epi + cfg["pragmatic_weight"] * prag
                     + cfg["consistency_weight"] * cons)
             traj = traj + (cfg["discount_factor"] ** t) * step
@@ -533,7 +533,7 @@ def free_energy_loss(score: Params, log_precision: torch.Tensor, states: torch.T
     complexity = 0.5 * torch.sum((states - prior_mean) ** 2 / (prior_std ** 2), dim=-1).mean()
     obs_err = torch.sum((observations - states) ** 2, dim=-1)
     accuracy = -0.5 * torch.exp(log_precision) * obs_err.mean()
-    s = score_forward(score, states, torch.full((B,), current_time), observations)
+    s = score_forward(score, states, torch.full((B,), current_time, device=states.device), observations)
     reg = 0.01 * torch.sum(s ** 2, dim=-1).mean()
     return complexity - accuracy + reg, {"complexity": complexity, "accuracy": -accuracy,
                                          "observation_error": obs_err.mean(),
