@@ -337,6 +337,9 @@ class DiffusionActiveInference(nn.Module):
     def _compute_latent_kl(self, latent: torch.Tensor, prior_latent: torch.Tensor) -> torch.Tensor:
         return 0.5 * torch.sum((latent - prior_latent) ** 2, dim=-1)
 
+    ELBO_KEYS = ["reconstruction_loss", "kl_loss", "score_matching_loss", "elbo", "reward_loss", "grad_penalty",
+                 "mean_time", "loss_weight_mean"]
+
     def compute_diffusion_elbo(self, observations: torch.Tensor, rewards: torch.Tensor,
                                latents: Optional[torch.Tensor] = None,
                                raw_observations: Optional[torch.Tensor] = None, *,
@@ -344,11 +347,27 @@ class DiffusionActiveInference(nn.Module):
                                prior_eps: Optional[torch.Tensor] = None):
         """-ELBO as written in the reference (signs included).  Keyword-only `t`,
         `noise`, `prior_eps` inject the reference's draws (rand / randn_like / randn_like)."""
+        loss, vals = self.elbo_device(observations, rewards, latents, raw_observations, t=t, noise=noise,
+                                      prior_eps=prior_eps)
+        vals = vals.cpu()                                                                   # one D2H
+        return loss, {k: float(v) for k, v in zip(self.ELBO_KEYS, vals)}
+
+    def elbo_device(self, observations: torch.Tensor, rewards: torch.Tensor,
+                    latents: Optional[torch.Tensor] = None, raw_observations: Optional[torch.Tensor] = None, *,
+                    t: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                    prior_eps: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """`compute_diffusion_elbo` without its device->host read: returns (loss, metrics[8] in
+        ELBO_KEYS order, both on the device).  With t drawn here there is no host synchronisation
+        anywhere in the loss, so forward + backward can be captured in a CUDA graph
+        (train_graph.GraphedElboStep)."""
         observations, rewards = observations.to(self.device), rewards.to(self.device)
         B, dev = observations.shape[0], self.device
         if latents is None:
             latents = self.update_belief_via_diffusion(observations, raw_observations)["latent"]
         recon = F.mse_loss(self.decode_observation(latents), observations)
+        # t drawn here lies in [0,1): the score net's continuous-time branch (score_networks.py:121)
+        # is known without reading the tensor back; an injected t is inspected as the reference does
+        continuous = True if t is None else None
         if t is None:
             t = self._importance_sample_time(B, dev) if hasattr(self, "time_importance_weights") \
                 else torch.rand(B, device=dev)
@@ -356,14 +375,15 @@ class DiffusionActiveInference(nn.Module):
             noise = torch.randn_like(latents)
         diff = self.latent_diffusion
         noisy, _, info_q = diff.continuous_q_sample(latents, t, noise)
-        score_fn = autograd_path.score_forward
-        pred = score_fn(self.latent_score_network, noisy, t, observations)
+        if continuous is None:
+            continuous = bool(t.max() <= 1.0 and t.min() >= 0.0)
+        pred = autograd_path.score_forward(self.latent_score_network, noisy, t, observations, continuous)
         sigma = info_q["sigma"]
         true_score = -noise / (sigma + 1e-8)
         w = diff.compute_loss_weight(t)
         per_sample = w.view(-1) * torch.sum((pred - true_score) ** 2, dim=1)
         sm = per_sample.mean()
-        gp = self._compute_gradient_penalty(noisy, t, observations)
+        gp = self._compute_gradient_penalty(noisy, t, observations, continuous)
         if prior_eps is None:
             prior = diff.sample_latent_prior(B, dev)
         else:
@@ -372,14 +392,15 @@ class DiffusionActiveInference(nn.Module):
         klw = torch.exp(-5.0 * t.mean())
         pr = autograd_path.seq(self.reward_predictor, latents)
         r_std = torch.exp(torch.clamp(pr[:, 1], min=-5, max=2))
-        rl = -torch.distributions.Normal(pr[:, 0], r_std).log_prob(rewards).mean()
+        # -log N(r; m, s) written out (torch.distributions validates its arguments with a host sync)
+        # (same expression as Normal.log_prob)
+        log_prob = -((rewards - pr[:, 0]) ** 2) / (2 * r_std ** 2) - r_std.log() - math.log(math.sqrt(2 * math.pi))
+        rl = -log_prob.mean()
         c = self.config
         elbo = -recon + c.kl_weight * kl * klw + c.diffusion_weight * sm + 0.1 * gp - c.reward_weight * rl
         self._update_time_importance(t, per_sample.detach())
-        vals = torch.stack([recon, kl, sm, elbo, rl, gp, t.mean(), w.mean()]).detach().cpu()   # one D2H
-        keys = ["reconstruction_loss", "kl_loss", "score_matching_loss", "elbo", "reward_loss", "grad_penalty",
-                "mean_time", "loss_weight_mean"]
-        return -elbo, {k: float(v) for k, v in zip(keys, vals)}
+        vals = torch.stack([recon, kl, sm, elbo, rl, gp, t.mean(), w.mean()]).detach()
+        return -elbo, vals
 
     def compute_lambda_returns(self, rewards: torch.Tensor, values: torch.Tensor, next_values: torch.Tensor,
                                dones: torch.Tensor, lambda_: float = 0.95, n_steps: int = 5,
@@ -390,9 +411,9 @@ class DiffusionActiveInference(nn.Module):
         return _lib.lambda_returns(rewards, next_values, dones, self.config.discount_factor, lambda_, n_steps,
                                    exclude_immediate_rewards)
 
-    def _compute_gradient_penalty(self, noisy_latents, t, observations) -> torch.Tensor:
+    def _compute_gradient_penalty(self, noisy_latents, t, observations, continuous: Optional[bool] = None) -> torch.Tensor:
         x = noisy_latents.detach().requires_grad_(True)
-        s = autograd_path.score_forward(self.latent_score_network, x, t, observations)
+        s = autograd_path.score_forward(self.latent_score_network, x, t, observations, continuous)
         g = torch.autograd.grad(outputs=s.sum(), inputs=x, create_graph=True, retain_graph=True)[0]
         return torch.mean((g.norm(2, dim=1) - 1.0) ** 2)
 
@@ -400,7 +421,14 @@ class DiffusionActiveInference(nn.Module):
         if not hasattr(self, "time_importance_weights"):
             self.time_importance_weights = torch.ones(100, device=device)
         probs = F.softmax(self.time_importance_weights, dim=0)
-        idx = torch.multinomial(probs, batch_size, replacement=True)
+        if getattr(self, "graph_safe_time_sampling", False) or torch.cuda.is_current_stream_capturing():
+            # torch.multinomial validates `probs` with a host read; inside a CUDA-graph capture (or
+            # when `graph_safe_time_sampling` is set) the same categorical draw is taken by inverse
+            # CDF: same distribution, a different use of the generator than torch.multinomial
+            cdf = torch.cumsum(probs, dim=0)
+            idx = torch.searchsorted(cdf, torch.rand(batch_size, device=device) * cdf[-1]).clamp_(max=probs.numel() - 1)
+        else:
+            idx = torch.multinomial(probs, batch_size, replacement=True)
         return (idx.float() + torch.rand(batch_size, device=device)) / 100.0
 
     def _update_time_importance(self, t: torch.Tensor, loss: torch.Tensor) -> None:

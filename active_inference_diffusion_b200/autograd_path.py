@@ -138,11 +138,14 @@ def _all_modulations(net, cond: torch.Tensor):
 
 
 def score_forward(net, z_t: torch.Tensor, time: torch.Tensor,
-                  observation: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  observation: Optional[torch.Tensor] = None, continuous: Optional[bool] = None) -> torch.Tensor:
     """models/score_networks.py:101-171 with torch ops (eval-mode obs_encoder: Dropout = identity,
-    the same contract as the fused path)."""
+    the same contract as the fused path).  `continuous` states which time branch (:121) applies
+    when the caller already knows it (the ELBO draws t in [0,1) itself); None reads it from `time`
+    as the reference does, which costs a host sync and cannot be captured in a CUDA graph."""
     H = net.hidden_dim
-    continuous = bool(time.max() <= 1.0 and time.min() >= 0.0)
+    if continuous is None:
+        continuous = bool(time.max() <= 1.0 and time.min() >= 0.0)
     if continuous:
         # continuous_time_embed.0 is Linear(1 -> E): an outer product, kept element-wise
         c0 = net.continuous_time_embed[0]

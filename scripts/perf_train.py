@@ -26,7 +26,6 @@ B = GB // world
 g = torch.Generator().manual_seed(1 + rank)
 obs, rew, lat = torch.randn(B, L, generator=g).to(dev), torch.randn(B, generator=g).to(dev), torch.randn(B, L, generator=g).to(dev)
 params = list(ai.latent_score_network.parameters()) + list(ai.latent_diffusion.parameters())
-ai._update_time_importance = lambda t, loss: None      # the B x .item() host loop is not part of the device step
 
 
 def step():
@@ -62,6 +61,15 @@ def timed(label):
 for prec in ("bf16", "bf16x3"):
     AP.set_precision(prec)
     timed(f"tcgen05 aid_gemm_nt [{prec}]")
+# the same step captured as one CUDA graph (train_graph.GraphedElboStep): no launch gaps, no host syncs
+from active_inference_diffusion_b200.train_graph import GraphedElboStep
+for prec in ("bf16", "bf16x3"):
+    AP.set_precision(prec)
+    gs = GraphedElboStep(ai, B, params=params)
+    eager_step, step = step, (lambda gs=gs: gs(obs, rew, lat)[0])
+    timed(f"CUDA-graph step     [{prec}]")
+    step = eager_step
+    del gs
 AP.set_precision("bf16x3")
 # the same graph with torch's own matmul (cuBLAS) for comparison on the same box
 AP.MatmulNT_apply_saved = AP.MatmulNT.apply

@@ -177,6 +177,52 @@ def test_diffusion_elbo_loss_and_grads(precision, tol):
     assert torch.equal((t.cuda() * 99).long().clamp(0, 99).cpu(), R.time_importance_bins(t))
 
 
+def test_graphed_elbo_step_matches_eager_step():
+    """train_graph.GraphedElboStep: one CUDA-graph replay = forward + backward +
+    double backward + time-importance EMA of compute_diffusion_elbo with no host sync.  From the
+    same generator state and EMA weights a replay must reproduce the eager step: same draws (the
+    graph consumes the Philox stream exactly as the eager kernels do), same kernels -> same loss,
+    metrics, gradients and updated time-importance weights."""
+    from active_inference_diffusion_b200.train_graph import GraphedElboStep
+    L, A, H, B = 32, 6, 128, 48
+    ai, nets, cfg = make_ai(L, A, H)
+    ai.eval()
+    ai.graph_safe_time_sampling = True        # eager path uses the capture-safe categorical draw too
+    g = gen(33)
+    obs, rew, lat = torch.randn(B, L, generator=g).cuda(), torch.randn(B, generator=g).cuda(), torch.randn(B, L, generator=g).cuda()
+    step = GraphedElboStep(ai, B, allreduce=False)
+    torch.cuda.manual_seed(7)
+    step(obs, rew, lat)                        # warm-up (creates the EMA weights) + capture + first replay
+    assert step.graph is not None
+    w0 = ai.time_importance_weights.clone()
+    torch.cuda.manual_seed(11)
+    loss_g, met_g = step(obs, rew, lat)
+    loss_g, met_g = loss_g.clone(), met_g.clone()
+    grads_g = [p.grad.clone() for p in step.params]
+    w_g = ai.time_importance_weights.clone()
+    assert torch.isfinite(loss_g) and all(torch.isfinite(x).all() for x in grads_g)
+    assert any(float(x.abs().max()) > 0 for x in grads_g)
+    assert not torch.equal(w_g, w0)
+    for p in ai.observation_decoder.parameters():          # discarded as in the reference (:225)
+        assert p.grad is None
+    ai.time_importance_weights.copy_(w0)
+    torch.cuda.manual_seed(11)
+    loss_e, met_e = step._eager()
+    assert abs(float(loss_g) - float(loss_e)) <= 1e-6 * abs(float(loss_e)), (float(loss_g), float(loss_e))
+    assert torch.allclose(met_g, met_e, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(w_g, ai.time_importance_weights, rtol=1e-6, atol=1e-7)
+    for a, p in zip(grads_g, step.params):
+        assert rel_l2(a, p.grad) < 1e-6
+    d = step.metrics_dict()
+    assert set(d) == set(ai.ELBO_KEYS) and 0.0 <= d["mean_time"] < 1.0
+    # a second seed gives a different draw of t through the same graph
+    torch.cuda.manual_seed(12)
+    _, met2 = step(obs, rew, lat)
+    assert float(met2[6]) != float(met_g[6])
+    with pytest.raises(ValueError):
+        step(obs[:5], rew[:5], lat[:5])
+
+
 def test_epistemic_estimator_matches_oracle_with_injected_draws():
     """FunctionSpaceEpistemicEstimator.forward (core/active_inference.py:940-1063 + decoder shim) on
     the tcgen05 GEMM path vs the oracle, with the reference's draws injected in its order."""
