@@ -279,12 +279,26 @@ struct LnArgs {
 __global__ void k_ln_act(const LnArgs a) {
   const int rt = blockIdx.x, kb = blockIdx.y, r = threadIdx.x;
   const int kb_total = (a.n + TILE_K - 1) / TILE_K;
+  // this block's 64 gamma / beta values: staged once in shared memory and read back as float4
+  // broadcasts (per-element __ldg was 128 uniform global loads per thread next to 16 data loads)
+  __shared__ float4 s_gb[32];
+  if (r < 32) {
+    const int c = kb * 64 + (r & 15) * 4;
+    const float* src = (r < 16) ? a.gamma : a.beta;
+    float4 v;
+    v.x = (c + 0 < a.n) ? __ldg(src + c + 0) : 0.f;
+    v.y = (c + 1 < a.n) ? __ldg(src + c + 1) : 0.f;
+    v.z = (c + 2 < a.n) ? __ldg(src + c + 2) : 0.f;
+    v.w = (c + 3 < a.n) ? __ldg(src + c + 3) : 0.f;
+    s_gb[r] = v;
+  }
   float sn = 0.f, mean = 0.f, m2 = 0.f;
   for (int p = 0; p < a.stats_nt; ++p) {
     float2 s = a.stats[((size_t)rt * a.stats_nt + p) * TILE_M + r];
     stats_merge(sn, mean, m2, (float)min(TILE_N, a.n - p * TILE_N), s.x, s.y);
   }
   const float rstd = rsqrtf(m2 / (float)a.n + 1e-5f);
+  __syncthreads();
 #pragma unroll
   for (int half = 0; half < 2; ++half) {   // unrolled: all 16 float4 loads of the 64 columns in flight
     float y[32];
@@ -298,11 +312,13 @@ __global__ void k_ln_act(const LnArgs a) {
       float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a.resid && c < a.ld4 * 4) rv = a.resid[((size_t)rt * a.ld4 + (c >> 2)) * TILE_M + r];
       const float rs[4] = {rv.x, rv.y, rv.z, rv.w};
+      const float4 g4 = s_gb[half * 8 + q], b4 = s_gb[16 + half * 8 + q];
+      const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float v = 0.f;
         if (c + i < a.n) {
-          v = (xs[i] - mean) * rstd * __ldg(a.gamma + c + i) + __ldg(a.beta + c + i);
+          v = (xs[i] - mean) * rstd * gs[i] + bs[i];
           v = act_apply(v, a.act) + rs[i];
         }
         y[q * 4 + i] = v;
