@@ -315,6 +315,37 @@ static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs e
   }
 }
 
+// Linear -> LayerNorm -> ReLU (+ residual) -> packed bf16 as ONE CTA-pair kernel (EPI_LNACT,
+// gemm2.cuh): layers of width exactly 512 (the EFE heads at the default hidden size).  The fp32
+// pre-activation never leaves TMEM; the two-kernel form (EPI_F32 + k_ln_act) wrote and re-read it
+// through HBM (268 MB per layer at 65,536 rows).  AID_FUSED_LN=0 selects the two-kernel form.
+static bool lnact_fusable(const PLin& w, int act) {
+  static const bool off = getenv("AID_FUSED_LN") && atoi(getenv("AID_FUSED_LN")) == 0;
+  return !off && use_pairs() && w.n == LN_COLS && w.n_tiles == 4 && w.nw == 1 && w.kb <= MAX_RES_KB &&
+         act == ACT_RELU;
+}
+static int launch_gemm_lnact(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs ea, cudaStream_t st,
+                             int* err_flag) {
+  GemmArgs ga;
+  memset(&ga.conv, 0, sizeof(ga.conv));
+  ga.A = A;
+  ga.B = w.w;
+  ga.row_tiles = row_tiles;
+  ga.kb = w.kb;
+  ga.kb_stride = w.kb;
+  ga.splits = 1;
+  ga.n_tiles = w.n_tiles;
+  ga.err = err_flag;
+  ea.split_rt = row_tiles;
+  static const int dbg = getenv("AID_DEBUG") ? atoi(getenv("AID_DEBUG")) : 0;
+  ga.debug = dbg & ~(1 | 1024);     // the epilogue-off / MMA-off knobs do not apply to this kernel
+  ea.debug = 0;
+  static thread_local unsigned flip = 0;
+  ga.reverse = (dbg & 8) ? 0 : (int)(flip++ & 1);
+  if (!ea.bias) ea.bias = w.b;
+  return launch_gemm2_inst<EPI_LNACT, true, ACT_RELU>(ga, ea, st);
+}
+
 // adaLN modulation -> next layer in one CTA-pair kernel (chain2.cuh), opt-in with AID_CHAIN=1.
 // Correct (the GPU suite passes with it) and it removes the 134 MB xn round trip per layer pair, but
 // in its first form it is slower than the two separate kernels (3.65 vs 3.15 ms per denoise step at

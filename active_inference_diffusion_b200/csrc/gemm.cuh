@@ -45,6 +45,8 @@ enum EpiKind : int {
   EPI_F32 = 1,    // y = acc + bias (+ resid)           -> tiled fp32 and/or row-major fp32 (+ LN partials)
   EPI_MODLN = 2,  // xn = LN(h)*(1+scale)+shift         -> packed bf16   (acc = [scale | shift])
   EPI_SCORE = 3,  // clamp/scale score, optional reverse-diffusion step -> z (fp32 row-major + packed)
+  EPI_LNACT = 4,  // y = act(LayerNorm(acc + bias) * gamma + beta) (+ resid) -> packed bf16; the whole
+                  // 512-column row is normalised from TMEM (CTA-pair kernel only, gemm2.cuh)
 };
 
 // Implicit im2col of a 3x3 / stride-1 / padding-1 convolution (encoder.inc): the A operand is the
@@ -94,6 +96,9 @@ struct EpiArgs {
   float* out_rm;             // optional row-major output [rows_valid, ld_rm]
   int ld_rm;
   int split_rt;              // row tiles per split (= row_tiles); out_rm row = rt*128 + r over all splits
+  // EPI_LNACT (resid_tiled / ld4 above: residual added AFTER the activation)
+  const float* ln_gamma;     // [n_valid]
+  const float* ln_beta;      // [n_valid]
   // EPI_MODLN
   const float4* h_tiled;     // [rt][h_ld4][128]
   int h_ld4;

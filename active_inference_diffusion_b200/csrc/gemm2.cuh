@@ -108,7 +108,12 @@ __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
 // build defines AID_STAGE_STORES.  Off by default: measured on B200 it is neutral for the adaLN and
 // attention kernels and slower for the MLP kernels (mlp.0 114 -> 125 us), because the two buffers
 // cost two of the six operand stages.  The GPU suite passes with it on.
+// EPI_LNACT keeps bias / gamma / beta of the 512 columns (6 KiB) and the double-buffered exchange of
+// the two epilogue groups' LayerNorm partials (4 KiB) in the same region.
+constexpr int LN_COLS = 4 * TILE_N;
+constexpr int LN_SMEM_BYTES = 3 * LN_COLS * 4 + 2 * 2 * TILE_M * 8;
 __host__ __device__ constexpr int gemm2_stage_bytes(int epi) {
+  if (epi == EPI_LNACT) return LN_SMEM_BYTES;
 #ifdef AID_STAGE_STORES
   return (epi == EPI_SCORE) ? 0 : 2 * TILE_BYTES;
 #else
@@ -128,7 +133,7 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
   uint8_t* smem = smem_raw + (base - raw_addr);
   Gemm2Ctrl* ctrl = reinterpret_cast<Gemm2Ctrl*>(smem);
   constexpr int STAGE_OUT = gemm2_stage_bytes(EPI);
-  constexpr bool STAGED = STAGE_OUT != 0;
+  constexpr bool STAGED = STAGE_OUT != 0 && EPI != EPI_LNACT;
   const uint32_t out_stage = base + SMEM_CTRL;                 // 2 x 16 KiB (one per epilogue group)
   const uint32_t a_smem = out_stage + STAGE_OUT;
   const uint32_t ring_smem = a_smem + (RES ? ga.kb * TILE_BYTES : 0);
@@ -146,8 +151,11 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
   // at the same time on neighbouring pairs and the second read of the A tiles hits L2 (with contiguous
   // ranges ncu showed mlp.2 reading 620 MB from DRAM for 404 MB of operands: the pair came back to
   // the same 1 MB of A ~35 us later, after ~200 MB of other traffic had gone through the 126 MB L2).
-  const int u_lo = (int)((long long)pair * num_units / num_pairs);
-  const int u_hi = (int)((long long)(pair + 1) * num_units / num_pairs);
+  // EPI_LNACT normalises whole rows: a pair always takes BOTH column groups of a row-tile pair.
+  const int u_lo = EPI == EPI_LNACT ? groups * (int)((long long)pair * rps / num_pairs)
+                                    : (int)((long long)pair * num_units / num_pairs);
+  const int u_hi = EPI == EPI_LNACT ? groups * (int)((long long)(pair + 1) * rps / num_pairs)
+                                    : (int)((long long)(pair + 1) * num_units / num_pairs);
   const int u_begin = 0;
   const int u_end = RES ? u_hi - u_lo : (num_units - pair + num_pairs - 1) / num_pairs;
 
@@ -342,6 +350,131 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       nt = ng * TU + q % TU;
     };
     const uint32_t leader_acc_empty = map_to_rank(smem_u32(&ctrl->acc_empty[0]), 0);
+    if constexpr (EPI == EPI_LNACT) {
+      // ---- Linear -> LayerNorm -> activation (+ residual) -> packed bf16, whole rows from TMEM ----
+      // n_tiles == 4: the two 256-column units of a row-tile pair are consecutive units of this
+      // pair, so after their MMAs all 512 columns of this CTA's 128 rows sit in the four TMEM
+      // slots.  Group eg owns tiles q = 4j + eg and 4j + 2 + eg.  Pass 1 reads both tiles and
+      // accumulates (mean, M2); the groups swap partials through shared memory; pass 2 re-reads the
+      // accumulators (TMEM reads are cheap: no HBM round trip of the fp32 pre-activation), normalises,
+      // applies the activation and writes the next layer's packed operand.  A slot is released as
+      // soon as its second read has completed, so the next row pair's MMAs overlap pass 2.
+      float* s_bias = reinterpret_cast<float*>(smem + SMEM_CTRL);
+      float* s_gamma = s_bias + LN_COLS;
+      float* s_beta = s_gamma + LN_COLS;
+      float2* xch = reinterpret_cast<float2*>(s_beta + LN_COLS);   // [parity][group][row]
+      for (int i = (int)threadIdx.x - 128; i < LN_COLS; i += 256) {
+        s_bias[i] = ea.bias ? __ldg(ea.bias + i) : 0.f;
+        s_gamma[i] = __ldg(ea.ln_gamma + i);
+        s_beta[i] = __ldg(ea.ln_beta + i);
+      }
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      const int n_rowpairs = (u_end - u_begin) / TU;
+      const float inv_n = 1.0f / (float)LN_COLS;
+#pragma unroll 1
+      for (int j = 0; j < n_rowpairs; ++j) {
+        int rt = 0, nt[2];
+        uint32_t tm[2];
+        AccRelease rel[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int q = 4 * j + 2 * h + eg;
+          coords(q, rt, nt[h]);
+          const int buf = q & 3, use = q >> 2;
+          mbar_wait(smem_u32(&ctrl->acc_full[buf]), use & 1, ga.err, 8);
+          tm[h] = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
+          rel[h] = AccRelease{rank == 0 ? smem_u32(&ctrl->acc_empty[buf]) : leader_acc_empty + buf * 8, rank != 0};
+        }
+        tc_fence_after();
+        const bool valid = rt < ga.row_tiles;                  // odd tail: rank 1 has no tile
+        // pass 1: statistics of this group's 256 columns
+        float sn = 0.f, smean = 0.f, sm2 = 0.f;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t raw[32];
+          tmem_ld32(tm[h], raw);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float y[32];
+            bias32_from_smem(s_bias + nt[h] * TILE_N, c * 32, y);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) add2(y[i], y[i + 1], __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+            if (c + 1 < 4) tmem_ld32(tm[h] + (c + 1) * 32, raw);
+            float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) s2 = __fadd2_rn(s2, make_float2(y[i], y[i + 1]));
+            const float m = (s2.x + s2.y) * (1.0f / 32.0f);
+            const float2 nm = make_float2(-m, -m);
+            float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float2 d = __fadd2_rn(make_float2(y[i], y[i + 1]), nm);
+              q2 = __ffma2_rn(d, d, q2);
+            }
+            stats_merge(sn, smean, sm2, 32.f, m, q2.x + q2.y);
+          }
+        }
+        float2* x = xch + (size_t)(j & 1) * 2 * TILE_M;
+        x[eg * TILE_M + r] = make_float2(smean, sm2);
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        {   // merge in a fixed order (group 0 then group 1) so both groups get identical statistics
+          const float2 a = x[r], b = x[TILE_M + r];
+          sn = 0.f; smean = 0.f; sm2 = 0.f;
+          stats_merge(sn, smean, sm2, 256.f, a.x, a.y);
+          stats_merge(sn, smean, sm2, 256.f, b.x, b.y);
+        }
+        const float rstd = rsqrtf(sm2 * inv_n + 1e-5f);
+        const float nmr = -smean * rstd;
+        // pass 2: normalise, activation, residual, packed store
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t raw[32];
+          tmem_ld32(tm[h], raw);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            const int n0 = nt[h] * TILE_N + c * 32;
+            float y[32];
+            bias32_from_smem(s_bias, n0, y);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) add2(y[i], y[i + 1], __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+            if (c + 1 < 4) tmem_ld32(tm[h] + (c + 1) * 32, raw);
+            else acc_release(rel[h]);                            // the tile's last read is complete
+            float4 rv[8];
+            const bool has_res = ea.resid_tiled != nullptr && valid;
+            if (has_res) {
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq)
+                rv[qq] = ea.resid_tiled[((size_t)rt * ea.ld4 + (n0 >> 2) + qq) * TILE_M + r];
+            }
+            const float4* gp = reinterpret_cast<const float4*>(s_gamma + n0);
+            const float4* bp = reinterpret_cast<const float4*>(s_beta + n0);
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+              const float4 g4 = gp[qq], b4 = bp[qq];
+              // (y - mean) * rstd * gamma + beta, as k_ln_act evaluates it
+              y[qq * 4 + 0] = fmaf(fmaf(y[qq * 4 + 0], rstd, nmr), g4.x, b4.x);
+              y[qq * 4 + 1] = fmaf(fmaf(y[qq * 4 + 1], rstd, nmr), g4.y, b4.y);
+              y[qq * 4 + 2] = fmaf(fmaf(y[qq * 4 + 2], rstd, nmr), g4.z, b4.z);
+              y[qq * 4 + 3] = fmaf(fmaf(y[qq * 4 + 3], rstd, nmr), g4.w, b4.w);
+            }
+            act_apply32_ct<ACT>(y);
+            if (has_res) {
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) {
+                y[qq * 4 + 0] += rv[qq].x; y[qq * 4 + 1] += rv[qq].y;
+                y[qq * 4 + 2] += rv[qq].z; y[qq * 4 + 3] += rv[qq].w;
+              }
+            }
+            if (valid) {
+              __nv_bfloat16* tile = ea.out_packed + (size_t)(rt * ea.out_kb + (n0 >> 6)) * TILE_ELEMS;
+              store_packed32(tile, r, n0 & 63, y);
+            }
+          }
+        }
+      }
+    } else {
     const Stage stg{STAGED ? out_stage + eg * TILE_BYTES : 0u, 1 + eg, r == 0};
     EpiState<EPI> st;
     int rt = 0, nt = 0;
@@ -374,6 +507,7 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
       }
     }
     if (STAGED && stg.leader) bulk_wait_all<0>();   // every staged tile has reached global memory
+    }
   }
 
   tc_fence_before();

@@ -59,6 +59,47 @@ def test_heads_standalone(L, A, H):
         assert rel_l2(rm, rm2) < BF16_TOL and rel_l2(rs, rs2) < BF16_TOL
 
 
+@pytest.mark.parametrize("B", [1, 300, 1300])
+def test_heads_fused_layernorm_kernel_ragged_batches(B):
+    """Width-512 head layers run Linear -> LayerNorm -> ReLU (+ residual) as ONE CTA-pair kernel
+    (EPI_LNACT: the row is normalised from TMEM).  Ragged batches: a single row, an odd number of
+    128-row tiles (the pair's second CTA has no tile), more row pairs than one CTA pair takes."""
+    L, A, H = 128, 6, 512
+    ai, nets, _ = make_ai(L, A, H)
+    g = gen(B)
+    z, a = torch.randn(B, L, generator=g), torch.randn(B, A, generator=g)
+    t = torch.full((B,), 2.0)
+    with torch.no_grad():
+        _, _, mean, std = R.policy_forward(nets["policy"], z, None)       # trunk: residual after the activation
+        _, _, dist = ai.policy_network(z.cuda(), deterministic=True)
+        assert rel_l2(dist.mean, mean) < BF16_TOL and rel_l2(dist.stddev, std) < BF16_TOL
+        assert rel_l2(ai.latent_dynamics(z.cuda(), a.cuda()), R.dynamics_forward(nets["dynamics"], z, a)) < BF16_TOL
+        assert rel_l2(ai.value_network(z.cuda(), t.cuda()), R.value_forward(nets["value"], z, t)) < BF16_TOL
+        rm, _ = ai.predict_reward_from_latent(z.cuda())
+        assert rel_l2(rm, R.reward_head(nets["reward"], z)[0]) < BF16_TOL
+
+
+def test_two_kernel_layernorm_form_subprocess():
+    """AID_FUSED_LN=0 (read once per process) keeps the EPI_F32 + k_ln_act form of the same layers;
+    both forms must agree with each other far inside the bf16 bound."""
+    import os, subprocess, sys
+    code = ("import torch, sys; sys.path.insert(0, '.');"
+            "from tests.test_gpu_efe import make_ai; ai, _, _ = make_ai(128, 6, 512);"
+            "g = torch.Generator().manual_seed(5); z = torch.randn(300, 128, generator=g).cuda();"
+            "torch.save(ai.policy_network(z, deterministic=True)[2].mean.cpu(), sys.argv[1])")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("1", "0"):
+        path = os.path.join(root, "gpurun_out", f"_ln_form_{flag}.pt")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        run = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, AID_FUSED_LN=flag), cwd=root,
+                             capture_output=True, text=True, timeout=300)
+        assert run.returncode == 0, run.stderr[-2000:]
+        outs.append(torch.load(path))
+        os.remove(path)
+    assert rel_l2(outs[0], outs[1]) < 5e-3, rel_l2(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("L,A,H,B,K,h", [(32, 6, 128, 50, 3, 4), (128, 6, 512, 256, 2, 5), (64, 17, 256, 9, 1, 15)])
 def test_efe_rollout_epistemic_off(L, A, H, B, K, h):
     ai, nets, cfg = make_ai(L, A, H)
