@@ -63,20 +63,33 @@ def test_heads_standalone(L, A, H):
 def test_heads_fused_layernorm_kernel_ragged_batches(B):
     """Width-512 head layers run Linear -> LayerNorm -> ReLU (+ residual) as ONE CTA-pair kernel
     (EPI_LNACT: the row is normalised from TMEM).  Ragged batches: a single row, an odd number of
-    128-row tiles (the pair's second CTA has no tile), more row pairs than one CTA pair takes."""
-    L, A, H = 128, 6, 512
+    128-row tiles (the pair's second CTA has no tile), more row pairs than one CTA pair takes.
+    Errors are normalised by the RMS row norm of the oracle over the full 1,300-row batch, so a
+    single row whose scalar output happens to be near zero does not inflate a relative error."""
+    L, A, H, N = 128, 6, 512, 1300
     ai, nets, _ = make_ai(L, A, H)
-    g = gen(B)
-    z, a = torch.randn(B, L, generator=g), torch.randn(B, A, generator=g)
-    t = torch.full((B,), 2.0)
+    g = gen(4)
+    z, a = torch.randn(N, L, generator=g), torch.randn(N, A, generator=g)
+    t = torch.full((N,), 2.0)
+
+    def err(got, want_all):
+        want_all = want_all.reshape(N, -1).double()
+        got = got.reshape(B, -1).double().cpu()
+        scale = float(want_all.norm() / N ** 0.5) * B ** 0.5
+        return float((got - want_all[:B]).norm()) / scale
+
     with torch.no_grad():
         _, _, mean, std = R.policy_forward(nets["policy"], z, None)       # trunk: residual after the activation
-        _, _, dist = ai.policy_network(z.cuda(), deterministic=True)
-        assert rel_l2(dist.mean, mean) < BF16_TOL and rel_l2(dist.stddev, std) < BF16_TOL
-        assert rel_l2(ai.latent_dynamics(z.cuda(), a.cuda()), R.dynamics_forward(nets["dynamics"], z, a)) < BF16_TOL
-        assert rel_l2(ai.value_network(z.cuda(), t.cuda()), R.value_forward(nets["value"], z, t)) < BF16_TOL
-        rm, _ = ai.predict_reward_from_latent(z.cuda())
-        assert rel_l2(rm, R.reward_head(nets["reward"], z)[0]) < BF16_TOL
+        _, _, dist = ai.policy_network(z[:B].cuda(), deterministic=True)
+        rm, _ = ai.predict_reward_from_latent(z[:B].cuda())
+        errs = {"policy mean": err(dist.mean, mean), "policy std": err(dist.stddev, std),
+                "dynamics": err(ai.latent_dynamics(z[:B].cuda(), a[:B].cuda()), R.dynamics_forward(nets["dynamics"], z, a)),
+                "value": err(ai.value_network(z[:B].cuda(), t[:B].cuda()), R.value_forward(nets["value"], z, t)),
+                "reward": err(rm, R.reward_head(nets["reward"], z)[0])}
+        assert all(e < BF16_TOL for e in errs.values()), errs
+        if B > 1:     # rows are independent: a row's result does not depend on the batch it is in
+            _, _, d1 = ai.policy_network(z[:1].cuda(), deterministic=True)
+            assert torch.equal(d1.mean[0], dist.mean[0])
 
 
 def test_two_kernel_layernorm_form_subprocess():
