@@ -377,13 +377,16 @@ class DiffusionActiveInference(nn.Module):
         noisy, _, info_q = diff.continuous_q_sample(latents, t, noise)
         if continuous is None:
             continuous = bool(t.max() <= 1.0 and t.min() >= 0.0)
-        pred = autograd_path.score_forward(self.latent_score_network, noisy, t, observations, continuous)
+        # the conditioning path (time embeddings, observation encoder, adaLN modulations) is the same
+        # for the score-matching forward and the gradient penalty's forward: evaluated once, shared
+        mod, time_weight = autograd_path.score_conditioning(self.latent_score_network, t, observations, B, continuous)
+        pred = autograd_path.score_from_conditioning(self.latent_score_network, noisy, mod, time_weight)
         sigma = info_q["sigma"]
         true_score = -noise / (sigma + 1e-8)
         w = diff.compute_loss_weight(t)
         per_sample = w.view(-1) * torch.sum((pred - true_score) ** 2, dim=1)
         sm = per_sample.mean()
-        gp = self._compute_gradient_penalty(noisy, t, observations, continuous)
+        gp = self._compute_gradient_penalty(noisy, t, observations, continuous, conditioning=(mod, time_weight))
         if prior_eps is None:
             prior = diff.sample_latent_prior(B, dev)
         else:
@@ -411,9 +414,13 @@ class DiffusionActiveInference(nn.Module):
         return _lib.lambda_returns(rewards, next_values, dones, self.config.discount_factor, lambda_, n_steps,
                                    exclude_immediate_rewards)
 
-    def _compute_gradient_penalty(self, noisy_latents, t, observations, continuous: Optional[bool] = None) -> torch.Tensor:
+    def _compute_gradient_penalty(self, noisy_latents, t, observations, continuous: Optional[bool] = None,
+                                  conditioning=None) -> torch.Tensor:
         x = noisy_latents.detach().requires_grad_(True)
-        s = autograd_path.score_forward(self.latent_score_network, x, t, observations, continuous)
+        if conditioning is None:
+            conditioning = autograd_path.score_conditioning(self.latent_score_network, t, observations,
+                                                            x.shape[0], continuous)
+        s = autograd_path.score_from_conditioning(self.latent_score_network, x, *conditioning)
         g = torch.autograd.grad(outputs=s.sum(), inputs=x, create_graph=True, retain_graph=True)[0]
         return torch.mean((g.norm(2, dim=1) - 1.0) ** 2)
 

@@ -122,27 +122,41 @@ def _time_embed(net, time: torch.Tensor) -> torch.Tensor:
     return linear(F.silu(linear(e, t1.weight, t1.bias)), t3.weight, t3.bias)
 
 
-def _ada_ln(x: torch.Tensor, scale_shift: torch.Tensor) -> torch.Tensor:
-    scale, shift = scale_shift.chunk(2, dim=-1)
-    return F.layer_norm(x, (x.shape[-1],), None, None, 1e-5) * (1 + scale) + shift
+def _ada_ln(x: torch.Tensor, scale1_shift: torch.Tensor) -> torch.Tensor:
+    """LN(x) * (1 + scale) + shift as one fused multiply-add on top of the LayerNorm; the `1 +` is
+    already inside `scale1_shift` (see _all_modulations)."""
+    scale1, shift = scale1_shift.chunk(2, dim=-1)
+    return torch.addcmul(shift, F.layer_norm(x, (x.shape[-1],), None, None, 1e-5), scale1)
 
 
 def _all_modulations(net, cond: torch.Tensor):
     """Every adaLN modulation of the forward (2 per block + the final one) reads the SAME
     conditioning, so they are ONE GEMM: SiLU(cond) x [W_1; W_2; ...]^T.  One operand pack and one
-    launch instead of 13 (and one input-gradient GEMM instead of 13 in the backward)."""
+    launch instead of 13 (and one input-gradient GEMM instead of 13 in the backward).  The `1 +` of
+    `(1 + scale)` (models/score_networks.py:269) is added to the scale half of the concatenated bias
+    (a 13,312-element op) instead of to 13 [B, H] tensors; gradients are unchanged (a constant)."""
     mods = [m for blk in net.transformer_blocks for m in (blk.norm1, blk.norm2)] + [net.norm_final]
+    H = net.hidden_dim
     w = torch.cat([m.adaLN_modulation[1].weight for m in mods], dim=0)
     b = torch.cat([m.adaLN_modulation[1].bias for m in mods], dim=0)
-    return linear(F.silu(cond), w, b).split(2 * net.hidden_dim, dim=-1)
+    one = torch.zeros(2 * H, device=b.device, dtype=b.dtype)
+    one[:H] = 1.0
+    b = b + one.repeat(len(mods))
+    return linear(F.silu(cond), w, b).split(2 * H, dim=-1)
 
 
-def score_forward(net, z_t: torch.Tensor, time: torch.Tensor,
-                  observation: Optional[torch.Tensor] = None, continuous: Optional[bool] = None) -> torch.Tensor:
-    """models/score_networks.py:101-171 with torch ops (eval-mode obs_encoder: Dropout = identity,
-    the same contract as the fused path).  `continuous` states which time branch (:121) applies
-    when the caller already knows it (the ELBO draws t in [0,1) itself); None reads it from `time`
-    as the reference does, which costs a host sync and cannot be captured in a CUDA graph."""
+def score_conditioning(net, time: torch.Tensor, observation: Optional[torch.Tensor], batch: int,
+                       continuous: Optional[bool] = None):
+    """Everything of models/score_networks.py:101-171 that does not depend on z_t: time embeddings
+    (:117-141), observation encoder (:143-149), and the 13 adaLN modulations of their sum.  Returns
+    (modulations, time_weight or None).  The ELBO evaluates the score net twice on the same (t,
+    observation) -- the score-matching term and the gradient penalty (core/active_inference.py:584,717)
+    -- so it computes this once and shares it: one [B,512]x[512,13312] modulation GEMM (16 % of a
+    forward's FLOPs) and one backward of it instead of two; autograd sums both branches' gradients
+    into the shared tensor, so the parameter gradients are the same sums.
+    `continuous` states which time branch (:121) applies when the caller already knows it (the ELBO
+    draws t in [0,1) itself); None reads it from `time` as the reference does, which costs a host
+    sync and cannot be captured in a CUDA graph."""
     H = net.hidden_dim
     if continuous is None:
         continuous = bool(time.max() <= 1.0 and time.min() >= 0.0)
@@ -161,9 +175,13 @@ def score_forward(net, z_t: torch.Tensor, time: torch.Tensor,
         o = F.silu(enc[5](linear(o, enc[4].weight, enc[4].bias)))
         o = enc[8](linear(o, enc[7].weight, enc[7].bias))
     else:
-        o = torch.zeros(z_t.shape[0], H, device=z_t.device)
-    cond = t_emb + o
-    mod = _all_modulations(net, cond)
+        o = torch.zeros(batch, H, device=time.device)
+    return _all_modulations(net, t_emb + o), time_weight
+
+
+def score_from_conditioning(net, z_t: torch.Tensor, mod, time_weight: Optional[torch.Tensor]) -> torch.Tensor:
+    """The z_t-dependent part of the forward: latent_proj, the DiT blocks, output head (:151-171)."""
+    H = net.hidden_dim
     h = linear(z_t, net.latent_proj.weight, net.latent_proj.bias)
     for i, blk in enumerate(net.transformer_blocks):
         att = blk.attention
@@ -174,6 +192,14 @@ def score_forward(net, z_t: torch.Tensor, time: torch.Tensor,
     s = _seq(net.output_proj, _ada_ln(h, mod[-1]))
     s = torch.clamp(s, min=-10, max=10) * net.output_multiplier
     return s * time_weight if time_weight is not None else s
+
+
+def score_forward(net, z_t: torch.Tensor, time: torch.Tensor,
+                  observation: Optional[torch.Tensor] = None, continuous: Optional[bool] = None) -> torch.Tensor:
+    """models/score_networks.py:101-171 with torch ops (eval-mode obs_encoder: Dropout = identity,
+    the same contract as the fused path)."""
+    mod, time_weight = score_conditioning(net, time, observation, z_t.shape[0], continuous)
+    return score_from_conditioning(net, z_t, mod, time_weight)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -961,6 +961,7 @@ __global__ void k_pack_strided(const float* __restrict__ src, long long rs, long
                                __nv_bfloat16* __restrict__ dst, int row_tiles, int kb_total, int nw,
                                int triple, int kreg) {
   size_t total = (size_t)row_tiles * kb_total * 1024;
+  const bool vec = cs == 1 && (rs & 3) == 0 && (reinterpret_cast<unsigned long long>(src) & 15ull) == 0;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     int rt, kb, r, ch;
@@ -978,11 +979,19 @@ __global__ void k_pack_strided(const float* __restrict__ src, long long rs, long
       want_lo = (triple == 1) ? (region == 2) : (region == 1);
     }
     float v[8];
+    if (vec && row < rows && c0 + 8 <= cols) {   // row-major, 16-byte aligned rows: two 128-bit loads
+      const float4* p = reinterpret_cast<const float4*>(src + (long long)row * rs + c0);
+      const float4 a = __ldg(p), b = __ldg(p + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float x = (row < rows && c0 + i < cols) ? __ldg(src + (long long)row * rs + (long long)(c0 + i) * cs) : 0.f;
-      if (want_lo) x -= __bfloat162float(__float2bfloat16_rn(x));
-      v[i] = x;
+      for (int i = 0; i < 8; ++i)
+        v[i] = (row < rows && c0 + i < cols) ? __ldg(src + (long long)row * rs + (long long)(c0 + i) * cs) : 0.f;
+    }
+    if (want_lo) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] -= __bfloat162float(__float2bfloat16_rn(v[i]));
     }
     store_chunk(dst, rt, kb, kb_total, r, ch, v, nw);
   }
