@@ -126,6 +126,13 @@ def _declare_misc(l: ctypes.CDLL) -> None:
                                      c_int32, c_int32, c_void_p, c_void_p]
 
 
+def _declare_colsum(l: ctypes.CDLL) -> None:
+    l.aid_colsum_workspace_bytes.restype = c_size_t
+    l.aid_colsum_workspace_bytes.argtypes = [c_int32, c_int32]
+    l.aid_colsum.restype = c_int32
+    l.aid_colsum.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]
+
+
 def _declare_encoder(l: ctypes.CDLL) -> None:
     D = POINTER(AidEncoderDims)
     l.aid_encoder_packed_bytes.restype = c_size_t
@@ -154,6 +161,7 @@ def lib() -> ctypes.CDLL:
         _declare_train(l)
         _declare_misc(l)
         _declare_encoder(l)
+        _declare_colsum(l)
         _lib = l
     return _lib
 
@@ -251,6 +259,26 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = Non
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     check(l.aid_gemm_nt(ptr(a), a.stride(0), a.stride(1), ptr(b), b.stride(0), b.stride(1), ptr(bias), ptr(out),
                         M, N, K, prec, ptr(ws), ws_bytes, stream_ptr(dev)), "aid_gemm_nt")
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """x.sum(0) of a 2-D fp32 tensor with unit column stride (aid_colsum, deterministic)."""
+    dev = require_cuda(x)
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.dim() != 2:
+        raise ValueError("colsum expects a 2-D tensor")
+    if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+        x = x.contiguous()
+    M, N = x.shape
+    out = torch.empty(N, dtype=torch.float32, device=dev)
+    if M == 0 or N == 0:
+        return out.zero_()
+    l = lib()
+    ws_bytes = l.aid_colsum_workspace_bytes(M, N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(l.aid_colsum(ptr(x), x.stride(0), M, N, ptr(out), ptr(ws), ws_bytes, stream_ptr(dev)), "aid_colsum")
     return out
 
 

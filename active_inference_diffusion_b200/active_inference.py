@@ -380,13 +380,14 @@ class DiffusionActiveInference(nn.Module):
         # the conditioning path (time embeddings, observation encoder, adaLN modulations) is the same
         # for the score-matching forward and the gradient penalty's forward: evaluated once, shared
         mod, time_weight = autograd_path.score_conditioning(self.latent_score_network, t, observations, B, continuous)
-        pred = autograd_path.score_from_conditioning(self.latent_score_network, noisy, mod, time_weight)
+        folds = autograd_path.fold_attention(self.latent_score_network)       # W_o W_v per block, shared too
+        pred = autograd_path.score_from_conditioning(self.latent_score_network, noisy, mod, time_weight, folds)
         sigma = info_q["sigma"]
         true_score = -noise / (sigma + 1e-8)
         w = diff.compute_loss_weight(t)
         per_sample = w.view(-1) * torch.sum((pred - true_score) ** 2, dim=1)
         sm = per_sample.mean()
-        gp = self._compute_gradient_penalty(noisy, t, observations, continuous, conditioning=(mod, time_weight))
+        gp = self._compute_gradient_penalty(noisy, t, observations, continuous, conditioning=(mod, time_weight, folds))
         if prior_eps is None:
             prior = diff.sample_latent_prior(B, dev)
         else:

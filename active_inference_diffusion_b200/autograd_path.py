@@ -69,6 +69,20 @@ class MatmulNT(torch.autograd.Function):
         return ga, gb
 
 
+class ColSum(torch.autograd.Function):
+    """g.sum(0) (bias gradients) through `aid_colsum`; its backward is a broadcast view, so the
+    gradient penalty's double backward differentiates through it."""
+
+    @staticmethod
+    def forward(ctx, g):
+        ctx.rows = g.shape[0]
+        return _lib.colsum(g)
+
+    @staticmethod
+    def backward(ctx, gg):
+        return gg.unsqueeze(0).expand(ctx.rows, gg.shape[0])
+
+
 class LinearNT(torch.autograd.Function):
     """x W^T + b with the bias added in the GEMM epilogue; gradients again through MatmulNT."""
 
@@ -82,7 +96,7 @@ class LinearNT(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         gx = MatmulNT.apply(g, weight.t()) if ctx.needs_input_grad[0] else None
         gw = MatmulNT.apply(g.t(), x.t()) if ctx.needs_input_grad[1] else None
-        gb = g.sum(0) if ctx.needs_input_grad[2] else None
+        gb = ColSum.apply(g) if ctx.needs_input_grad[2] else None
         return gx, gw, gb
 
 
@@ -179,15 +193,33 @@ def score_conditioning(net, time: torch.Tensor, observation: Optional[torch.Tens
     return _all_modulations(net, t_emb + o), time_weight
 
 
-def score_from_conditioning(net, z_t: torch.Tensor, mod, time_weight: Optional[torch.Tensor]) -> torch.Tensor:
-    """The z_t-dependent part of the forward: latent_proj, the DiT blocks, output head (:151-171)."""
+def fold_attention(net):
+    """nn.MultiheadAttention over ONE token has softmax == 1, so attn(x) = W_o (W_v x + b_v) + b_o =
+    (W_o W_v) x + (W_o b_v + b_o) (models/score_networks.py:214-224; the inference kernels use the
+    same fold).  The fold is a differentiable H x H x H product of the parameters, so the training
+    graph runs ONE batch-sized GEMM per block instead of two (and one input-/weight-gradient pair
+    instead of two); the chain rule through the fold gives in_proj_weight[2H:], in_proj_bias[2H:],
+    out_proj.weight and out_proj.bias exactly the gradients of the two-GEMM form.
+    Returns [(W_f [H,H], b_f [H])] per block."""
     H = net.hidden_dim
+    folds = []
+    for blk in net.transformer_blocks:
+        att = blk.attention
+        w_v, b_v = att.in_proj_weight[2 * H:], att.in_proj_bias[2 * H:]
+        w_o, b_o = att.out_proj.weight, att.out_proj.bias
+        folds.append((linear(w_o, w_v.t()), torch.mv(w_o, b_v) + b_o))
+    return folds
+
+
+def score_from_conditioning(net, z_t: torch.Tensor, mod, time_weight: Optional[torch.Tensor],
+                            folds=None) -> torch.Tensor:
+    """The z_t-dependent part of the forward: latent_proj, the DiT blocks, output head (:151-171)."""
+    if folds is None:
+        folds = fold_attention(net)
     h = linear(z_t, net.latent_proj.weight, net.latent_proj.bias)
     for i, blk in enumerate(net.transformer_blocks):
-        att = blk.attention
-        x = _ada_ln(h, mod[2 * i])
-        v = linear(x, att.in_proj_weight[2 * H:], att.in_proj_bias[2 * H:])   # seq-len-1 attention == out(V x)
-        h = h + linear(v, att.out_proj.weight, att.out_proj.bias)
+        w_f, b_f = folds[i]
+        h = h + linear(_ada_ln(h, mod[2 * i]), w_f, b_f)          # seq-len-1 attention, folded
         h = h + _seq(blk.mlp, _ada_ln(h, mod[2 * i + 1]))
     s = _seq(net.output_proj, _ada_ln(h, mod[-1]))
     s = torch.clamp(s, min=-10, max=10) * net.output_multiplier

@@ -202,6 +202,15 @@ int32_t aid_fp_belief_update(const double* mean, const double* variance, const d
                              double noise_scale, double min_variance, double max_variance,
                              double* mean_out, double* variance_out, double* precision_out, void* stream);
 
+/* ---- bias gradients of the training graph ------------------------------------------------------
+ * out[n] = sum_m x[m*row_stride + n] (fp32, deterministic two-stage reduction): the `grad.sum(0)` of
+ * every nn.Linear bias in the backward of compute_diffusion_elbo (core/active_inference.py:584-606;
+ * autograd's generic reduction ran at ~1 TB/s on these [batch, N] tensors).  workspace: caller-owned,
+ * aid_colsum_workspace_bytes(M, N) bytes. */
+size_t aid_colsum_workspace_bytes(int32_t M, int32_t N);
+int32_t aid_colsum(const float* x, int64_t row_stride, int32_t M, int32_t N, float* out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* ---- _update_time_importance — core/active_inference.py:750-771 -----------------------------
  * weights[bin(t_i)] <- 0.99*w + 0.01*loss_i for i = 0..n-1 in batch order (double arithmetic, fp32
  * storage after every step, exactly as the reference's .item() loop), bin(t) =

@@ -78,6 +78,28 @@ def test_matmul_nt_first_and_second_derivatives():
         assert rel_l2(gt, wt) < 2e-2, (name, rel_l2(gt, wt))    # bf16 operand rounding (2^-9 per product)
 
 
+@pytest.mark.parametrize("M,N", [(1, 1), (7, 5), (300, 130), (4096, 512), (32768, 2048), (1000, 13312)])
+def test_colsum_matches_fp64_sum_and_is_deterministic(M, N):
+    """aid_colsum = grad.sum(0) of the Linear biases (two-stage, fixed order), incl. row-strided views."""
+    from active_inference_diffusion_b200 import _lib, autograd_path as AP
+    g = gen(M + N)
+    x = torch.randn(M, N, generator=g).cuda()
+    want = x.double().sum(0)
+    got = _lib.colsum(x)
+    assert float((got.double() - want).abs().max()) <= 1e-5 * (float(want.abs().max()) + M ** 0.5)
+    assert torch.equal(got, _lib.colsum(x))
+    if N >= 8:                                   # a column slice: row stride > N, unaligned start
+        v = x[:, 3:N - 1]
+        assert torch.allclose(_lib.colsum(v).double(), v.double().sum(0), rtol=1e-5, atol=1e-5 * M ** 0.5)
+    # autograd: first derivative is a broadcast, and it composes under create_graph
+    y = x[: min(M, 64)].clone().requires_grad_(True)
+    s = AP.ColSum.apply(y * y)
+    (gy,) = torch.autograd.grad(s.sum(), y, create_graph=True)
+    assert torch.allclose(gy, 2 * y)
+    gy.sum().backward()
+    assert torch.allclose(y.grad, torch.full_like(y, 2.0))
+
+
 def test_pair_kernel_variant_subprocess():
     """The cta_group::2 kernels are opt-in via AID_PAIRS=1 (read once per process)."""
     import os, subprocess, sys
