@@ -131,6 +131,8 @@ def _declare_colsum(l: ctypes.CDLL) -> None:
     l.aid_colsum_workspace_bytes.argtypes = [c_int32, c_int32]
     l.aid_colsum.restype = c_int32
     l.aid_colsum.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]
+    l.aid_gelu_double_backward.restype = c_int32
+    l.aid_gelu_double_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
 
 
 def _declare_encoder(l: ctypes.CDLL) -> None:
@@ -279,6 +281,18 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     ws_bytes = l.aid_colsum_workspace_bytes(M, N)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     check(l.aid_colsum(ptr(x), x.stride(0), M, N, ptr(out), ptr(ws), ws_bytes, stream_ptr(dev)), "aid_colsum")
+    return out
+
+
+def gelu_double_backward(gg: torch.Tensor, g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """gg * g * phi(x) * (2 - x^2), element-wise (aid_gelu_double_backward)."""
+    dev = require_cuda(gg, g, x)
+    gg, g, x = f32c(gg), f32c(g), f32c(x)
+    if not (gg.shape == g.shape == x.shape):
+        raise ValueError("gelu_double_backward: shapes differ")
+    out = torch.empty_like(x)
+    check(lib().aid_gelu_double_backward(ptr(gg), ptr(g), ptr(x), ptr(out), x.numel(), stream_ptr(dev)),
+          "aid_gelu_double_backward")
     return out
 
 

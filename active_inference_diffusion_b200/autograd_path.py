@@ -100,6 +100,37 @@ class LinearNT(torch.autograd.Function):
         return gx, gw, gb
 
 
+class GeluBackward(torch.autograd.Function):
+    """g * gelu'(x) (torch's fused kernel) whose own backward -- needed only by the gradient penalty's
+    double backward -- is two kernels: gelu_backward(gg, x) and aid_gelu_double_backward.  Autograd's
+    composite formula for the same derivative is ~10 element-wise kernels on [B, 4H] tensors."""
+
+    @staticmethod
+    def forward(ctx, g, x):
+        ctx.save_for_backward(g, x)
+        return torch.ops.aten.gelu_backward(g, x)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gg):
+        g, x = ctx.saved_tensors
+        return torch.ops.aten.gelu_backward(gg, x), _lib.gelu_double_backward(gg, g, x)
+
+
+class Gelu(torch.autograd.Function):
+    """Exact (erf) GELU, models/score_networks.py:199, differentiable twice through GeluBackward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return F.gelu(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return GeluBackward.apply(g, x)
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """F.linear with the contraction (and the bias add) on the tcgen05 path."""
     if bias is None:
@@ -114,6 +145,8 @@ def _seq(mods, x: torch.Tensor) -> torch.Tensor:
             x = linear(x, m.weight, m.bias)
         elif isinstance(m, torch.nn.Sequential):
             x = _seq(m, x)
+        elif isinstance(m, torch.nn.GELU) and m.approximate == "none" and x.is_cuda:
+            x = Gelu.apply(x)
         else:
             x = m(x)
     return x

@@ -211,6 +211,13 @@ size_t aid_colsum_workspace_bytes(int32_t M, int32_t N);
 int32_t aid_colsum(const float* x, int64_t row_stride, int32_t M, int32_t N, float* out, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* out[i] = gg[i] * g[i] * phi(x[i]) * (2 - x[i]^2), phi = standard normal density: the derivative of
+ * gelu_backward(g, x) = g * d/dx[x Phi(x)] with respect to x, contracted with gg -- the one term of the
+ * gradient penalty's double backward (core/active_inference.py:709-729) through nn.GELU
+ * (models/score_networks.py:199) that autograd otherwise evaluates as ~10 element-wise kernels. */
+int32_t aid_gelu_double_backward(const float* gg, const float* g, const float* x, float* out, int64_t n,
+                                 void* stream);
+
 /* ---- _update_time_importance — core/active_inference.py:750-771 -----------------------------
  * weights[bin(t_i)] <- 0.99*w + 0.01*loss_i for i = 0..n-1 in batch order (double arithmetic, fp32
  * storage after every step, exactly as the reference's .item() loop), bin(t) =

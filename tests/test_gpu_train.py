@@ -100,6 +100,28 @@ def test_colsum_matches_fp64_sum_and_is_deterministic(M, N):
     assert torch.allclose(y.grad, torch.full_like(y, 2.0))
 
 
+def test_gelu_function_first_and_second_derivatives():
+    """autograd_path.Gelu: value, gradient and the double-backward terms (aid_gelu_double_backward) vs
+    torch's own exact GELU in fp64 under create_graph."""
+    from active_inference_diffusion_b200 import autograd_path as AP
+    g = gen(8)
+    x0 = torch.randn(257, 131, generator=g) * 2
+    v0 = torch.randn(257, 131, generator=g)
+
+    def run(fn, dev, dt):
+        x = x0.to(dev, dt).requires_grad_(True)
+        v = v0.to(dev, dt).requires_grad_(True)
+        y = fn(x) * v
+        (gx,) = torch.autograd.grad(y.sum(), x, create_graph=True)
+        ((gx ** 2).sum() + y.sum()).backward()
+        return [t.detach().double().cpu() for t in (y, gx, x.grad, v.grad)]
+
+    want = run(torch.nn.functional.gelu, "cpu", torch.float64)
+    got = run(AP.Gelu.apply, "cuda", torch.float32)
+    for name, a, b in zip(("y", "dy/dx", "x.grad", "v.grad"), got, want):
+        assert rel_l2(a, b) < 1e-5, (name, rel_l2(a, b))
+
+
 def test_pair_kernel_variant_subprocess():
     """The cta_group::2 kernels are opt-in via AID_PAIRS=1 (read once per process)."""
     import os, subprocess, sys
