@@ -126,6 +126,9 @@ class LatentDiffusionProcess(nn.Module):
         dev = _lib.require_cuda(z_init, observation, noise)
         z_init, observation, noise = _lib.f32c(z_init), _lib.f32c(observation), _lib.f32c(noise)
         batch, n_steps = z_init.shape[0], len(step_times)
+        if batch == 0:                  # empty batch: T+1 empty latents, as the reference's loop gives
+            traj = z_init.new_empty(n_steps + 1, 0, self.latent_dim) if return_trajectory else None
+            return torch.empty_like(z_init), traj
         T = int(self.betas.shape[0])
         coef = self.reverse_coefficients()
         packed = score_network.packed_weights()

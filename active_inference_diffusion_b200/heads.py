@@ -214,6 +214,8 @@ class HeadsBundle:
         d = self.dims()
         width = {0: 2 * d.action_dim, 1: d.latent_dim, 2: 1, 3: 2}[which]
         out = torch.empty(B, width, dtype=torch.float32, device=dev)
+        if B == 0:                      # empty batch: empty result, as the reference's modules give
+            return out
         packed, ws = self.packed_weights(), self.workspace(B, dev)
         _lib.check(_lib.lib().aid_head_forward(ctypes.byref(d), packed.data_ptr(), ws.data_ptr(), ws.numel(), which,
                                                B, z.data_ptr(), _lib.ptr(aux), out.data_ptr(), _lib.stream_ptr(dev)),
@@ -238,6 +240,8 @@ class HeadsBundle:
         first = torch.empty(B, d.action_dim, dtype=torch.float32, device=dev)
         prag = torch.empty(K, B, dtype=torch.float32, device=dev)
         cons = torch.empty(K, B, dtype=torch.float32, device=dev)
+        if B == 0:
+            return efe, first, prag, cons
         c = _lib.AidEfeConfig(cfg["epistemic_weight"], cfg["pragmatic_weight"], cfg["consistency_weight"],
                               cfg["discount_factor"])
         packed, ws = self.packed_weights(), self.workspace(B, dev)

@@ -175,6 +175,8 @@ class LatentScoreNetwork(nn.Module):
             return autograd_path.score_forward(self, _lib.f32c(z_t), _lib.f32c(time), _lib.f32c(observation))
         z_t, time, observation = _lib.f32c(z_t), _lib.f32c(time), _lib.f32c(observation)
         batch = z_t.shape[0]
+        if batch == 0:                  # empty batch: empty score, as the reference module gives
+            return torch.empty(0, self.latent_dim, dtype=torch.float32, device=dev)
         continuous = bool(time.max() <= 1.0 and time.min() >= 0.0)
         packed = self.packed_weights()
         ws = self.workspace(batch, batch, dev)

@@ -185,3 +185,22 @@ def test_alternative_kernel_families_subprocess(env):
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), cwd=root, capture_output=True,
                          text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
+
+
+def test_empty_batch_returns_empty_results():
+    """B = 0 (an empty candidate set / replay slice): empty outputs of the right shapes from the score
+    forward, the sampler, the heads and the EFE rollout, as the reference's torch modules give."""
+    from active_inference_diffusion_b200 import (ActiveInferenceConfig, CandidateScorer, DiffusionConfig)
+    L, O, A, H, T = 32, 17, 6, 128, 4
+    torch.manual_seed(0)
+    cfg = ActiveInferenceConfig(latent_dim=L, hidden_dim=H, efe_horizon=3, device="cpu",
+                                diffusion=DiffusionConfig(num_diffusion_steps=T))
+    m = CandidateScorer(O, A, cfg).eval().cuda()
+    obs = torch.empty(0, O, device="cuda")
+    with torch.no_grad():
+        s = m.latent_score_network(torch.empty(0, L, device="cuda"), torch.empty(0, device="cuda"), obs)
+        assert s.shape == (0, L)
+        traj = m.latent_diffusion.generate_latent_trajectory(m.latent_score_network, 0, obs)
+        assert len(traj) == T + 1 and all(t.shape == (0, L) for t in traj)
+        efe, first, latent = m(obs, horizon=3, num_trajectories=2)
+        assert efe.shape == (0,) and first.shape == (0, A) and latent.shape == (0, L)
