@@ -380,17 +380,21 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
         for (int h = 0; h < 2; ++h) {
           const int q = 4 * j + 2 * h + eg;
           coords(q, rt, nt[h]);
-          const int buf = q & 3, use = q >> 2;
-          mbar_wait(smem_u32(&ctrl->acc_full[buf]), use & 1, ga.err, 8);
+          const int buf = q & 3;
           tm[h] = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TILE_N);
           rel[h] = AccRelease{rank == 0 ? smem_u32(&ctrl->acc_empty[buf]) : leader_acc_empty + buf * 8, rank != 0};
         }
-        tc_fence_after();
         const bool valid = rt < ga.row_tiles;                  // odd tail: rank 1 has no tile
-        // pass 1: statistics of this group's 256 columns
+        // pass 1: statistics of this group's 256 columns (the first unit's tile is read while the
+        // second unit's MMAs are still running)
         float sn = 0.f, smean = 0.f, sm2 = 0.f;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
+          {
+            const int q = 4 * j + 2 * h + eg;
+            mbar_wait(smem_u32(&ctrl->acc_full[q & 3]), (q >> 2) & 1, ga.err, 8);
+            tc_fence_after();
+          }
           uint32_t raw[32];
           tmem_ld32(tm[h], raw);
 #pragma unroll 1
@@ -450,14 +454,16 @@ gemm2_kernel(const GemmArgs ga, const EpiArgs ea, const int ring_stages) {
             }
             const float4* gp = reinterpret_cast<const float4*>(s_gamma + n0);
             const float4* bp = reinterpret_cast<const float4*>(s_beta + n0);
+            const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(nmr, nmr);
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) {
               const float4 g4 = gp[qq], b4 = bp[qq];
-              // (y - mean) * rstd * gamma + beta, as k_ln_act evaluates it
-              y[qq * 4 + 0] = fmaf(fmaf(y[qq * 4 + 0], rstd, nmr), g4.x, b4.x);
-              y[qq * 4 + 1] = fmaf(fmaf(y[qq * 4 + 1], rstd, nmr), g4.y, b4.y);
-              y[qq * 4 + 2] = fmaf(fmaf(y[qq * 4 + 2], rstd, nmr), g4.z, b4.z);
-              y[qq * 4 + 3] = fmaf(fmaf(y[qq * 4 + 3], rstd, nmr), g4.w, b4.w);
+              // ((y - mean) * rstd) * gamma + beta on register pairs (FFMA2)
+              const float2 t0 = __ffma2_rn(make_float2(y[qq * 4 + 0], y[qq * 4 + 1]), rs2, nm2);
+              const float2 t1 = __ffma2_rn(make_float2(y[qq * 4 + 2], y[qq * 4 + 3]), rs2, nm2);
+              const float2 o0 = __ffma2_rn(t0, make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+              const float2 o1 = __ffma2_rn(t1, make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+              y[qq * 4 + 0] = o0.x; y[qq * 4 + 1] = o0.y; y[qq * 4 + 2] = o1.x; y[qq * 4 + 3] = o1.y;
             }
             act_apply32_ct<ACT>(y);
             if (has_res) {
