@@ -54,18 +54,21 @@ def set_precision(name: str) -> None:
 
 class MatmulNT(torch.autograd.Function):
     """out[M,N] = a[M,K] @ b[N,K]^T through `aid_gemm_nt`.  d/da = g @ b, d/db = g^T @ a, both again
-    MatmulNT on transposed views, hence differentiable to any order."""
+    MatmulNT on transposed views, hence differentiable to any order.  The backward GEMMs run at the
+    precision the forward ran at (a `with precision(...)` region may have ended by then)."""
 
     @staticmethod
     def forward(ctx, a, b):
         ctx.save_for_backward(a, b)
+        ctx.prec = PRECISION
         return _lib.gemm_nt(a, b, precision=PRECISION)
 
     @staticmethod
     def backward(ctx, g):
         a, b = ctx.saved_tensors
-        ga = MatmulNT.apply(g, b.t()) if ctx.needs_input_grad[0] else None
-        gb = MatmulNT.apply(g.t(), a.t()) if ctx.needs_input_grad[1] else None
+        with precision(ctx.prec):
+            ga = MatmulNT.apply(g, b.t()) if ctx.needs_input_grad[0] else None
+            gb = MatmulNT.apply(g.t(), a.t()) if ctx.needs_input_grad[1] else None
         return ga, gb
 
 
@@ -89,13 +92,15 @@ class LinearNT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
+        ctx.prec = PRECISION
         return _lib.gemm_nt(x, weight, bias, precision=PRECISION)
 
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
-        gx = MatmulNT.apply(g, weight.t()) if ctx.needs_input_grad[0] else None
-        gw = MatmulNT.apply(g.t(), x.t()) if ctx.needs_input_grad[1] else None
+        with precision(ctx.prec):
+            gx = MatmulNT.apply(g, weight.t()) if ctx.needs_input_grad[0] else None
+            gw = MatmulNT.apply(g.t(), x.t()) if ctx.needs_input_grad[1] else None
         gb = ColSum.apply(g) if ctx.needs_input_grad[2] else None
         return gx, gw, gb
 

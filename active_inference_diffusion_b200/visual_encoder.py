@@ -9,9 +9,14 @@ conventions.  The forward pass is one `aid_encoder_forward` call: the four 3x3 c
 attention, the LayerNorms and the small projection tail are fused element-wise kernels around them
 (layout in `csrc/encoder.inc`).
 
-Scope of this round: the eval-mode forward (what `DiffusionPixelAgent.act`, the collector and
-evaluation use).  The training-mode forward (dropout masks, one power iteration per call) and the
-backward pass are not implemented; calling the module in training mode raises.
+The fused kernels are the inference path (eval mode under no recorded graph: what
+`DiffusionPixelAgent.act`, the collector and evaluation use).  In training mode -- or when the
+input requires grad -- the module evaluates the reference's forward as a differentiable graph
+(`_forward_autograd`): Dropout2d / Dropout masks and the spectral-norm power iteration behave as in
+the reference, the 117 M-parameter `Linear(conv_out_dim -> 2F)` and `Linear(2F -> F)` run forward,
+input-gradient and weight-gradient on the tcgen05 `aid_gemm_nt` path; the 3x3 convolutions and
+their gradients use torch's conv ops in this round (hand-written conv backward kernels are the
+remaining part of SURVEY §8 f-1).
 """
 from __future__ import annotations
 
@@ -170,13 +175,28 @@ class DrQV2Encoder(nn.Module):
             raise ValueError(f"Expected observations of shape {self.obs_shape}, got {tuple(x.shape[1:])}")
         return x
 
+    def _forward_autograd(self, x: torch.Tensor) -> torch.Tensor:
+        """visual_encoders.py:166-189 as a differentiable graph (training mode / input gradients)."""
+        from . import autograd_path
+        F = torch.nn.functional
+        _lib.require_cuda(x)
+        x = x.float() / 255.0 if x.dtype == torch.uint8 else x.float()
+        for i in range(self.num_layers):
+            x = F.mish(self.norms[i](self.convs[i](x)))
+            if i + 1 < self.num_layers:
+                x = self.dropouts[i](x)
+        if self.use_attention:           # SpatialAttention.forward, :210-224
+            att = self.attention
+            pooled = torch.cat([x.mean(dim=1, keepdim=True), x.max(dim=1, keepdim=True)[0]], dim=1)
+            x = x + x * torch.sigmoid(att.spatial_conv(pooled) / att.temperature)
+        x = self.ln(x.reshape(x.shape[0], -1))
+        with autograd_path.precision("bf16x3" if self.precision == "bf16x3" else "bf16"):
+            return autograd_path.seq(self.output_layers, x)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self.training:
-            raise NotImplementedError(
-                "DrQV2Encoder: only the eval-mode forward runs on the sm_100a path this round "
-                "(training-mode dropout / power iteration / backward are SURVEY §8 f-1 follow-ups); "
-                "call .eval()")
         x = self._canonical_input(x)
+        if self.training or (torch.is_grad_enabled() and x.requires_grad):
+            return self._forward_autograd(x)
         dev = _lib.require_cuda(x)
         is_u8 = x.dtype == torch.uint8
         x = x.contiguous() if is_u8 else _lib.f32c(x)

@@ -105,9 +105,11 @@ def test_encoder_input_conventions_and_errors():
         enc(torch.rand(2, d["frame_stack"] + 1, c, h, w).cuda())
     with pytest.raises(RuntimeError):
         enc(torch.rand(2, d["frame_stack"] * c, h, w))                   # CPU tensor: no fallback
-    enc.train()
-    with pytest.raises(NotImplementedError):
-        enc(one)
+    enc.train()                                                          # training mode: differentiable graph
+    out = enc(one)
+    assert out.shape == (1, d["feature_dim"]) and out.requires_grad
+    with pytest.raises(RuntimeError):
+        enc(torch.rand(2, d["frame_stack"] * c, h, w))                   # still no CPU fallback
 
 
 @pytest.mark.parametrize("env", [{"AID_ENC_IMPLICIT": "0"}, {"AID_ENC_CHUNK": "2"}])
@@ -140,3 +142,52 @@ def test_encoder_alternative_paths_subprocess(env):
             outs[tag] = {f: torch.load(os.path.join(tmp, f)) for f in sorted(os.listdir(tmp)) if f.startswith(tag)}
         for (ka, va), (kd, vd) in zip(sorted(outs["alt"].items()), sorted(outs["default"].items())):
             assert torch.equal(va, vd), (ka, kd, float((va - vd).abs().max()))
+
+
+def test_encoder_training_mode_and_gradients():
+    """Differentiable evaluation (training mode / input gradients): features equal the fused kernels',
+    input and parameter gradients equal the oracle restatement's under fp32 autograd (the two Linear
+    layers run forward / dgrad / wgrad on aid_gemm_nt, bf16x3); training mode draws dropout masks and
+    advances the spectral-norm power iteration as the reference module does."""
+    fx = torch.load(os.path.join(GOLD, "encoder_small.pt"), weights_only=False)
+    enc = build(fx["dims"], fx["weights"], "bf16x3")
+    x0 = next(iter(fx["inputs"].values()))
+    x0 = R.encoder_canonical_input(x0, fx["dims"]["obs_shape"][0], fx["dims"]["frame_stack"]).float().cuda()
+    with torch.no_grad():
+        fused = enc(x0)
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        xg = x0.clone().requires_grad_(True)
+        out = enc(xg)                                  # eval mode + input gradient -> autograd graph
+        assert rel_l2(out, fused) < 1e-3
+        w = torch.randn(out.shape, generator=gen(3)).cuda()
+        (out * w).sum().backward()
+        p = {k: (v.cuda().clone().requires_grad_(True) if v.is_floating_point() else v.cuda())
+             for k, v in fx["weights"].items()}
+        xo = x0.clone().requires_grad_(True)
+        want = R.encoder_forward(p, xo)
+        (want * w).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    assert rel_l2(out, want) < 1e-3
+    assert rel_l2(xg.grad, xo.grad) < 2e-3, rel_l2(xg.grad, xo.grad)
+    named = dict(enc.named_parameters())
+    checked = 0
+    for k in ("output_layers.0.weight", "output_layers.0.bias", "output_layers.4.weight", "ln.weight",
+              "convs.0.weight_orig", "convs.3.weight_orig", "norms.2.weight", "attention.spatial_conv.weight"):
+        if k in named and k in p and p[k].grad is not None:
+            assert rel_l2(named[k].grad, p[k].grad) < 2e-3, (k, rel_l2(named[k].grad, p[k].grad))
+            checked += 1
+    assert checked >= 6
+    # training mode
+    enc.train()
+    u0 = enc.convs[1].weight_u.clone()
+    torch.manual_seed(0)
+    a = enc(x0)
+    b = enc(x0)
+    assert a.shape == fused.shape and torch.isfinite(a).all() and not torch.equal(a, b)   # dropout masks differ
+    assert not torch.equal(enc.convs[1].weight_u, u0)                                     # power iteration ran
+    a.sum().backward()
+    assert enc.output_layers[0].weight.grad is not None
