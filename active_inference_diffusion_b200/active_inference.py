@@ -349,6 +349,7 @@ class DiffusionActiveInference(nn.Module):
         `noise`, `prior_eps` inject the reference's draws (rand / randn_like / randn_like)."""
         loss, vals = self.elbo_device(observations, rewards, latents, raw_observations, t=t, noise=noise,
                                       prior_eps=prior_eps)
+        self._join_time_importance()
         vals = vals.cpu()                                                                   # one D2H
         return loss, {k: float(v) for k, v in zip(self.ELBO_KEYS, vals)}
 
@@ -428,6 +429,7 @@ class DiffusionActiveInference(nn.Module):
     def _importance_sample_time(self, batch_size: int, device: torch.device) -> torch.Tensor:
         if not hasattr(self, "time_importance_weights"):
             self.time_importance_weights = torch.ones(100, device=device)
+        self._join_time_importance()
         probs = F.softmax(self.time_importance_weights, dim=0)
         if getattr(self, "graph_safe_time_sampling", False) or torch.cuda.is_current_stream_capturing():
             # torch.multinomial validates `probs` with a host read; inside a CUDA-graph capture (or
@@ -451,4 +453,26 @@ class DiffusionActiveInference(nn.Module):
         if w.device != t.device or w.dtype != torch.float32 or not w.is_contiguous():
             w = w.to(t.device, torch.float32).contiguous()
             self.time_importance_weights = w
-        _lib.time_importance_update(t, loss, w)
+        # The EMA only feeds the NEXT call's time sampling, and its per-bin chains are sequential
+        # (1.8 ms at 32,768 samples once importance sampling has concentrated the batch in a few
+        # bins), so it runs on a side stream beside the backward pass; `_join_time_importance` orders
+        # it before anything that reads the weights.
+        _lib.require_cuda(t, loss)
+        main = torch.cuda.current_stream(t.device)
+        side = getattr(self, "_ti_stream", None)
+        if side is None or side.device != t.device:
+            side = self._ti_stream = torch.cuda.Stream(device=t.device)
+        t, loss = t.detach(), loss.detach()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _lib.time_importance_update(t, loss, w)
+        if not torch.cuda.is_current_stream_capturing():
+            t.record_stream(side)
+            loss.record_stream(side)
+        self._ti_pending = True
+
+    def _join_time_importance(self) -> None:
+        """Make the current stream wait for a pending time-importance update."""
+        if getattr(self, "_ti_pending", False):
+            torch.cuda.current_stream(self._ti_stream.device).wait_stream(self._ti_stream)
+            self._ti_pending = False

@@ -62,6 +62,7 @@ class GraphedElboStep:
             p.grad = None
         loss, vals = self.ai.elbo_device(self.obs, self.rewards, self.latents)
         loss.backward()
+        self.ai._join_time_importance()   # the EMA ran beside the backward on its side stream
         for p in self._others:        # decoder / reward-head gradients are discarded (reference :225)
             p.grad = None
         return loss.detach(), vals
