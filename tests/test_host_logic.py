@@ -113,3 +113,67 @@ def test_shard_bounds_partition():
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_training_graph_algebra_matches_oracle_on_cpu(monkeypatch):
+    """The graph-level rewrites of the training forward (conditioning path shared between the two
+    score evaluations, `1 + scale` folded into the modulation bias, single-token attention folded to
+    W_o W_v) are algebra, independent of the GEMM kernel: with `autograd_path.linear` replaced by
+    F.linear the CPU graph must reproduce the oracle's score and every parameter gradient, first
+    order and through the gradient penalty's double backward (core/active_inference.py:709-729)."""
+    import torch.nn.functional as F
+    from active_inference_diffusion_b200 import autograd_path as AP
+    from oracle import restatement as R
+    from tests.util import gen, make_score_net, rel_l2
+    monkeypatch.setattr(AP, "linear", lambda x, w, b=None: F.linear(x, w, b))
+    L, O, H, NB, B = 16, 5, 32, 2, 9
+    net, params = make_score_net(L, O, H, NB)
+    net = net.double()
+    g = gen(4)
+    z = torch.randn(B, L, generator=g, dtype=torch.float64)
+    obs = torch.randn(B, O, generator=g, dtype=torch.float64)
+    for t in (torch.rand(B, generator=g, dtype=torch.float64), torch.full((B,), 7.0, dtype=torch.float64)):
+        p = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in params.items()}
+
+        def penalised(score_fn):
+            x = z.clone().requires_grad_(True)
+            s = score_fn(x)
+            (gx,) = torch.autograd.grad(s.sum(), x, create_graph=True)
+            return s, (s ** 2).mean() + ((gx.norm(2, dim=1) - 1.0) ** 2).mean()
+
+        s_want, loss_want = penalised(lambda x: R.score_forward(p, x, t, obs))
+        loss_want.backward()
+        # one conditioning + one fold shared by the evaluation (as compute_diffusion_elbo does)
+        mod, tw = AP.score_conditioning(net, t, obs, B)
+        folds = AP.fold_attention(net)
+        s_got, loss_got = penalised(lambda x: AP.score_from_conditioning(net, x, mod, tw, folds))
+        for q in net.parameters():
+            q.grad = None
+        loss_got.backward()
+        assert rel_l2(s_got, s_want) < 1e-10
+        assert abs(float(loss_got) - float(loss_want)) < 1e-10 * abs(float(loss_want))
+        checked = 0
+        for k, q in net.named_parameters():
+            if q.grad is None or p[k].grad is None:
+                continue
+            if float(p[k].grad.abs().max()) == 0.0:
+                assert float(q.grad.abs().max()) < 1e-12, k
+                continue
+            assert rel_l2(q.grad, p[k].grad) < 1e-8, (k, rel_l2(q.grad, p[k].grad))
+            checked += 1
+        assert checked > 20
+
+
+def test_graphed_step_and_colsum_fail_loudly_without_cuda():
+    """No CPU fallback for the training step either."""
+    from active_inference_diffusion_b200 import _lib
+    from active_inference_diffusion_b200.train_graph import GraphedElboStep
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError):
+        GraphedElboStep(object(), 8)
+    with pytest.raises(RuntimeError):
+        _lib.colsum(torch.zeros(4, 4))
+    with pytest.raises(RuntimeError):
+        _lib.gelu_double_backward(torch.zeros(4), torch.zeros(4), torch.zeros(4))
+    assert _lib.lib().aid_colsum_workspace_bytes(1000, 512) >= 512 * 4
