@@ -1,0 +1,117 @@
+// Probe for DESIGN.md §8b item 2(a): can the weight-gradient GEMM of the training step read the
+// ROW-MAJOR packed operands (the tiles the forward / input-gradient GEMMs already made) as MN-major
+// tcgen05 operands, so that no transposed pack is needed?
+//
+//   dW[n, k] = sum_m g[m, n] * x[m, k]        (contraction over the batch rows m)
+//
+// Packed tile of this library: [16-byte chunk c (8 features)][row r (128)][8 bf16], i.e. element
+// (feature f = 8c + j, row r) at byte c*2048 + r*16 + j*2.  Read with MN = feature, K = row this is
+// the MN-major no-swizzle canonical layout ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO)) of
+// cute/atom/mma_traits_sm100.hpp with T = 8, SBO = 2048 B (next 8-feature chunk), LBO = 128 B (next
+// 8 rows); one K = 16 MMA advances the start address by 256 B.  Instruction descriptor: a_major
+// (bit 15) = b_major (bit 16) = 1.
+//
+// The probe builds A = g tile (128 rows x 128 features) and B = x tile (128 rows x 256 features) in
+// that layout, issues the eight K=16 MMAs of one 128-row K-block, reads D[128 x 256] back from TMEM
+// and compares with the host product.  NOT RUN YET (written at the end of round 1 without GPU
+// budget left): build + run
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scripts/micro/mn_major_probe scripts/micro/mn_major_probe.cu
+//   ./scripts/micro/mn_major_probe        -> prints the max abs error; ~1e-6 relative means the
+//                                            descriptor reading above is right.
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include "../../active_inference_diffusion_b200/csrc/ptx.cuh"
+using namespace aid;
+
+constexpr int ROWS = 128;          // batch rows of the K-block (contraction)
+constexpr int FA = 128;            // features of the A operand (g: N_out slice) -> MMA M
+constexpr int FB = 256;            // features of the B operand (x: K_in slice)  -> MMA N
+constexpr int A_BYTES = (FA / 8) * ROWS * 16;   // 32 KiB
+constexpr int B_BYTES = (FB / 8) * ROWS * 16;   // 64 KiB
+
+__device__ __forceinline__ uint64_t desc_mn_nosw(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+__global__ void __launch_bounds__(128, 1) probe(const uint8_t* a_packed, const uint8_t* b_packed, float* d_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tbase;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  for (int i = threadIdx.x; i < A_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(a_packed)[i];
+  for (int i = threadIdx.x; i < B_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem + A_BYTES)[i] = reinterpret_cast<const uint4*>(b_packed)[i];
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tbase), 256); tmem_relinquish(); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(FA, FB) | (1u << 15) | (1u << 16);   // A and B MN-major
+    for (int k = 0; k < ROWS / 16; ++k) {
+      const uint64_t ad = desc_mn_nosw(base + k * 256, 128, ROWS * 16);
+      const uint64_t bd = desc_mn_nosw(base + A_BYTES + k * 256, 128, ROWS * 16);
+      umma_bf16(tbase, ad, bd, idesc, k ? 1u : 0u);
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0, nullptr, 0);
+  tc_fence_after();
+  // thread = TMEM lane = D row m (feature of A); 256 columns (features of B)
+  const int m = threadIdx.x;
+  const uint32_t tm = tbase + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+  for (int c = 0; c < FB / 32; ++c) {
+    uint32_t raw[32];
+    tmem_ld32(tm + c * 32, raw);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) d_out[(size_t)m * FB + c * 32 + j] = __uint_as_float(raw[j]);
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tbase, 256);
+}
+
+static void pack(const std::vector<float>& src, int feats, std::vector<__nv_bfloat16>& dst) {
+  dst.resize((size_t)feats * ROWS);
+  for (int f = 0; f < feats; ++f)
+    for (int r = 0; r < ROWS; ++r)
+      dst[(size_t)(f / 8) * ROWS * 8 + (size_t)r * 8 + (f % 8)] = __float2bfloat16(src[(size_t)r * feats + f]);
+}
+
+int main() {
+  std::vector<float> g((size_t)ROWS * FA), x((size_t)ROWS * FB);
+  srand(1);
+  for (auto& v : g) v = (rand() % 2001 - 1000) / 1000.0f;
+  for (auto& v : x) v = (rand() % 2001 - 1000) / 1000.0f;
+  std::vector<__nv_bfloat16> gp, xp;
+  pack(g, FA, gp);
+  pack(x, FB, xp);
+  uint8_t *da, *db;
+  float* dd;
+  cudaMalloc(&da, A_BYTES); cudaMalloc(&db, B_BYTES); cudaMalloc(&dd, (size_t)FA * FB * 4);
+  cudaMemcpy(da, gp.data(), A_BYTES, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, xp.data(), B_BYTES, cudaMemcpyHostToDevice);
+  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, A_BYTES + B_BYTES + 2048);
+  probe<<<1, 128, A_BYTES + B_BYTES + 2048>>>(da, db, dd);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+  std::vector<float> d((size_t)FA * FB);
+  cudaMemcpy(d.data(), dd, d.size() * 4, cudaMemcpyDeviceToHost);
+  double worst = 0, scale = 0;
+  for (int m = 0; m < FA; ++m)
+    for (int n = 0; n < FB; ++n) {
+      double acc = 0;
+      for (int r = 0; r < ROWS; ++r)
+        acc += (double)__bfloat162float(__float2bfloat16(g[(size_t)r * FA + m])) *
+               (double)__bfloat162float(__float2bfloat16(x[(size_t)r * FB + n]));
+      worst = fmax(worst, fabs(acc - d[(size_t)m * FB + n]));
+      scale = fmax(scale, fabs(acc));
+    }
+  printf("MN-major probe: max |err| = %.3e (max |ref| = %.3f) -> %s\n", worst, scale,
+         worst < 1e-3 * scale ? "descriptor reading confirmed" : "MISMATCH");
+  return worst < 1e-3 * scale ? 0 : 2;
+}
