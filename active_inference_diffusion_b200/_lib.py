@@ -13,7 +13,47 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaid_sm100.so")
+# One source tree, one shared library per tensor-core operand type (csrc/gemm.cuh, pack_op16x2):
+#   "bf16": bf16 operands (8-bit significand), stated bf16 bounds (precision)
+#   "f16" : IEEE fp16 operands (11-bit significand = the TF32 significand) at the same tensor-pipe
+#           rate: the rel-1e-3 ("fp32/TF32") contract of the sampled latents, EFE, losses, gradients
+LIB_PATHS = {"bf16": os.path.join(_HERE, "libaid_sm100.so"), "f16": os.path.join(_HERE, "libaid_sm100_f16.so")}
+LIB_PATH = LIB_PATHS["bf16"]
+ABI_VERSION = 2
+OPERAND_TYPES = tuple(LIB_PATHS)
+_operand = os.environ.get("AID_PRECISION", "bf16")
+if _operand not in LIB_PATHS:
+    raise RuntimeError(f"AID_PRECISION={_operand!r}: expected one of {sorted(LIB_PATHS)}")
+
+
+def operand_type() -> str:
+    """Operand type the fused inference calls (score forward, sampler, EFE rollout, heads, encoder)
+    use on this thread of control: "bf16" or "f16"."""
+    return _operand
+
+
+def set_operand_type(name: str) -> str:
+    """Select the tensor-core operand type of the fused calls; returns the previous one."""
+    global _operand
+    if name not in LIB_PATHS:
+        raise ValueError(f"unknown operand type {name!r}; expected one of {sorted(LIB_PATHS)}")
+    prev, _operand = _operand, name
+    return prev
+
+
+class operand:
+    """`with _lib.operand("f16"):` — operand type for a region."""
+
+    def __init__(self, name: str):
+        if name not in LIB_PATHS:
+            raise ValueError(f"unknown operand type {name!r}; expected one of {sorted(LIB_PATHS)}")
+        self.name = name
+
+    def __enter__(self):
+        self.prev = set_operand_type(self.name)
+
+    def __exit__(self, *exc):
+        set_operand_type(self.prev)
 
 
 class AidScoreDims(ctypes.Structure):
@@ -30,6 +70,11 @@ class AidEncoderDims(ctypes.Structure):
     _fields_ = [("in_channels", c_int32), ("height", c_int32), ("width", c_int32),
                 ("num_filters", c_int32), ("num_layers", c_int32), ("feature_dim", c_int32),
                 ("use_attention", c_int32), ("precision", c_int32)]
+
+
+class AidSampleNoise(ctypes.Structure):
+    _fields_ = [("z_init", c_void_p), ("noise", c_void_p), ("philox", c_void_p), ("row_offset", c_int64),
+                ("deterministic", c_int32)]
 
 
 class AidEfeConfig(ctypes.Structure):
@@ -59,7 +104,7 @@ SCORE_BLOCK_KEYS = [
     "mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias",
 ]
 
-_lib: Optional[ctypes.CDLL] = None
+_libs: dict = {}
 
 
 def _declare(l: ctypes.CDLL) -> None:
@@ -135,6 +180,17 @@ def _declare_colsum(l: ctypes.CDLL) -> None:
     l.aid_gelu_double_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
 
 
+def _declare_r2(l: ctypes.CDLL) -> None:
+    """Round-2 entry points (include/aid_b200.h)."""
+    l.aid_operand_type.restype = c_int32
+    l.aid_sample_ex.restype = c_int32
+    l.aid_sample_ex.argtypes = [POINTER(AidScoreDims), c_void_p, c_void_p, c_size_t, c_int32, c_int32,
+                                POINTER(c_float), POINTER(c_int32), POINTER(c_float), c_int32, c_void_p,
+                                POINTER(AidSampleNoise), c_void_p, c_void_p, c_void_p]
+    l.aid_philox_normal.restype = c_int32
+    l.aid_philox_normal.argtypes = [c_void_p, ctypes.c_uint32, c_int64, c_void_p, c_int32, c_int32, c_void_p]
+
+
 def _declare_encoder(l: ctypes.CDLL) -> None:
     D = POINTER(AidEncoderDims)
     l.aid_encoder_packed_bytes.restype = c_size_t
@@ -150,27 +206,33 @@ def _declare_encoder(l: ctypes.CDLL) -> None:
                                       c_void_p]
 
 
-def lib() -> ctypes.CDLL:
-    """Load the CUDA extension; fail loudly when it has not been built."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def lib(operand_type: Optional[str] = None) -> ctypes.CDLL:
+    """Load the CUDA extension of the given (default: current) operand type; fail loudly when it
+    has not been built."""
+    name = operand_type or _operand
+    l = _libs.get(name)
+    if l is None:
+        path = LIB_PATHS[name]
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; "
                 "g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
-        l = ctypes.CDLL(LIB_PATH)
+        l = ctypes.CDLL(path)
         _declare(l)
         _declare_train(l)
         _declare_misc(l)
         _declare_encoder(l)
         _declare_colsum(l)
-        _lib = l
-    return _lib
+        _declare_r2(l)
+        if l.aid_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{path}: ABI version {l.aid_abi_version()} != {ABI_VERSION}; rebuild")
+        _libs[name] = l
+    return l
 
 
-def check(rc: int, what: str) -> None:
+def check(rc: int, what: str, l: Optional[ctypes.CDLL] = None) -> None:
     if rc != 0:
-        msg = lib().aid_last_error().decode("utf-8", "replace")
+        msg = (l or lib()).aid_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed: {msg}")
 
 
@@ -186,6 +248,56 @@ def require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
     if dev is None:
         raise RuntimeError("no tensor given")
     return dev
+
+
+class PackedCache:
+    """Derived caches of a parameter-holding module: packed tensor-core operand tiles (one entry per
+    operand type and device) and scratch workspaces (one per device and stream, so a collector
+    thread and the trainer never share scratch memory).
+
+    A pack is rebuilt when the identity or the autograd version counter of any parameter changes
+    (optimizer steps, `load_state_dict`, `.to()` all bump one of them).  In-place edits through
+    `.data` (`p.data.copy_()`, `p.data.mul_()` — the EMA / target-sync idiom) do NOT bump the
+    version counter: call `invalidate()` (modules expose it as `invalidate_packed()`) after them.
+    `verify=True` (or AID_VERIFY_PACKED=1) additionally compares a device-side checksum of the
+    parameters with the one taken at pack time; it costs a host read per call and is meant for
+    debugging and tests."""
+
+    VERIFY = os.environ.get("AID_VERIFY_PACKED", "0") not in ("", "0")
+
+    def __init__(self):
+        self.entries: dict = {}
+        self.scratch: dict = {}
+
+    def invalidate(self) -> None:
+        self.entries.clear()
+
+    @staticmethod
+    def _checksum(params) -> torch.Tensor:
+        live = [p.detach().double().sum() for p in params if p is not None]
+        return torch.stack(live).sum() if live else torch.zeros((), dtype=torch.float64)
+
+    def get(self, tag, params, build, verify: bool = False) -> torch.Tensor:
+        """`build()` -> packed tensor; cached under `tag` (operand type, precision ...)."""
+        live = [p for p in params if p is not None]
+        dev = require_cuda(*live)
+        key = tuple((p.data_ptr(), p._version) for p in live)
+        full = (tag, dev)
+        hit = self.entries.get(full)
+        check = verify or self.VERIFY
+        if hit is not None and hit[0] == key:
+            if not check or bool(self._checksum(live) == hit[2]):
+                return hit[1]
+        packed = build()
+        self.entries[full] = (key, packed, self._checksum(live) if check else None)
+        return packed
+
+    def workspace(self, need: int, device: torch.device) -> torch.Tensor:
+        sk = (device, torch.cuda.current_stream(device).cuda_stream)
+        ws = self.scratch.get(sk)
+        if ws is None or ws.numel() < need:
+            ws = self.scratch[sk] = torch.empty(need, dtype=torch.uint8, device=device)
+        return ws
 
 
 def f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -237,14 +349,15 @@ def _strided_2d(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
-PRECISIONS = {"bf16": 0, "bf16x3": 1}
+# training-graph GEMM precisions: (operand type = which library, hi/lo split along K)
+PRECISIONS = {"bf16": ("bf16", 0), "bf16x3": ("bf16", 1), "f16": ("f16", 0)}
 
 
 def gemm_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None,
             precision: str = "bf16") -> torch.Tensor:
     """out[M,N] = a[M,K] @ b[N,K]^T (+ bias) on the tcgen05 path; a and b may be transposed views.
     precision "bf16" rounds the operands to bf16; "bf16x3" uses the hi/lo split (fp32-class products)."""
-    prec = PRECISIONS[precision]
+    op, prec = PRECISIONS[precision]
     dev = require_cuda(a, b, bias)
     a, b, bias = _strided_2d(a), _strided_2d(b), f32c(bias)
     M, K = a.shape
@@ -256,11 +369,12 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = Non
         return out
     if K == 0:
         return out.zero_() if bias is None else out.copy_(bias.expand(M, N))
-    l = lib()
+    l = lib(op)
     ws_bytes = l.aid_gemm_nt_workspace_bytes(M, N, K, prec)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(l.aid_gemm_nt(ptr(a), a.stride(0), a.stride(1), ptr(b), b.stride(0), b.stride(1), ptr(bias), ptr(out),
-                        M, N, K, prec, ptr(ws), ws_bytes, stream_ptr(dev)), "aid_gemm_nt")
+    with torch.cuda.device(dev):
+        check(l.aid_gemm_nt(ptr(a), a.stride(0), a.stride(1), ptr(b), b.stride(0), b.stride(1), ptr(bias), ptr(out),
+                            M, N, K, prec, ptr(ws), ws_bytes, stream_ptr(dev)), "aid_gemm_nt", l)
     return out
 
 

@@ -189,7 +189,20 @@ class DiffusionActiveInference(nn.Module):
             self.device = p.device
             if hasattr(self, "epistemic_estimator"):
                 self.epistemic_estimator.device = p.device
+        if hasattr(self, "_heads"):
+            self._heads.invalidate_packed()
         return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_packed()
+        return out
+
+    def invalidate_packed(self) -> None:
+        """Drop every derived packed-weight cache (score net, EFE heads).  Needed after in-place
+        parameter edits through `.data` (EMA / target sync idiom), which no version counter sees."""
+        self.latent_score_network.invalidate_packed()
+        self._heads.invalidate_packed()
 
     # ---- small heads ---------------------------------------------------------------------
     def decode_observation(self, latent: torch.Tensor, decode_to_pixels: bool = True) -> torch.Tensor:

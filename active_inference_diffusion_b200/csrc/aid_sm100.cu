@@ -47,13 +47,15 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 static int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  static int sms[64] = {0};   // per device: one process may drive several GPUs
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev] = n;
   }
-  return sms;
+  return sms[dev];
 }
 
 static int ew_grid(size_t work_items, int block = 256) {
@@ -682,6 +684,9 @@ struct StepOut {
   float tw_scalar = 1.0f;
   const float* z_in = nullptr;
   const float* eps = nullptr;
+  const PhiloxState* philox = nullptr;
+  unsigned philox_draw = 0;
+  long long row_offset = 0;
   float c_s1 = 0, c_ra = 0, c_c1 = 0, c_c2 = 0, c_sigma = 0;
   float* z_out = nullptr;
   __nv_bfloat16* z_packed_out = nullptr;
@@ -754,6 +759,7 @@ static int run_score_trunk(const ScoreW& s, ScoreWS& w, const StepOut& o, cudaSt
   e.n_valid = s.L; e.rows_valid = w.B;
   e.out_mult = s.out_mult; e.tw_rows = o.tw_rows; e.tw_scalar = o.tw_scalar;
   e.do_step = o.do_step; e.z_in = o.z_in; e.eps = o.eps;
+  e.philox = o.philox; e.philox_draw = o.philox_draw; e.row_offset = o.row_offset;
   e.c_s1 = o.c_s1; e.c_ra = o.c_ra; e.c_c1 = o.c_c1; e.c_c2 = o.c_c2; e.c_sigma = o.c_sigma;
   e.z_out = o.z_out; e.out_packed = o.z_packed_out; e.out_kb = ceil_div(s.L, 64);
   AID_TRY(launch_gemm<EPI_SCORE>(reinterpret_cast<uint8_t*>(w.o1), w.RT, s.out2, e, st, w.err));
@@ -811,16 +817,58 @@ extern "C" int32_t aid_score_forward(const AidScoreDims* dims, const void* packe
 
 // ------------------------------------------------------------------------------------------
 // Reverse diffusion
-extern "C" int32_t aid_sample(const AidScoreDims* dims, const void* packed, void* workspace,
-                              size_t workspace_bytes, int32_t batch, int32_t n_steps,
-                              const float* step_time_host, const int32_t* step_index_host,
-                              const float* coef_host, int32_t T, const float* observation,
-                              const float* z_init, const float* noise, float* z_out, float* traj_out,
-                              void* stream) {
+// Per-step time arguments of the score net's two branches (models/score_networks.py:121-137), same
+// fp32 operations as the reference's tensor ops.  The step times travel as kernel parameters (no
+// host-memory copy), which keeps aid_sample capturable in a CUDA graph.
+struct StepTimes {
+  float t[128];
+};
+__global__ void k_step_time_args(const StepTimes st, int n, int base, float* __restrict__ sin_arg,
+                                 float* __restrict__ t_norm, float* __restrict__ flag) {
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  const float ti = st.t[i];
+  const bool cont = (ti <= 1.0f) && (ti >= 0.0f);
+  sin_arg[base + i] = cont ? __fmul_rn(ti, 999.0f) : ti;
+  t_norm[base + i] = cont ? __fsub_rn(__fmul_rn(2.0f, ti), 1.0f) : 0.f;
+  flag[base + i] = cont ? 1.f : 0.f;
+}
+
+// z_T (or any [rows, cols] block of standard normals) from the Philox stream of philox.cuh
+__global__ void k_philox_normal(const PhiloxState* __restrict__ state, unsigned int draw, long long row_offset,
+                                float* __restrict__ out, int rows, int cols4) {
+  const PhiloxState ps = *state;
+  const size_t total = (size_t)rows * cols4;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / cols4), c4 = (int)(idx % cols4);
+    reinterpret_cast<float4*>(out)[idx] =
+        philox_normal4(ps, draw, (unsigned long long)(row_offset + row), (uint32_t)c4);
+  }
+}
+
+extern "C" int32_t aid_philox_normal(const void* philox, uint32_t draw, int64_t row_offset, float* out,
+                                     int32_t rows, int32_t cols, void* stream) {
+  if (!philox || !out) return fail("aid_philox_normal: null pointer");
+  if (rows <= 0 || cols <= 0 || (cols & 3)) return fail("aid_philox_normal: rows > 0 and cols a positive multiple of 4");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_philox_normal<<<ew_grid((size_t)rows * (cols / 4)), 256, 0, st>>>(static_cast<const PhiloxState*>(philox), draw,
+                                                                     row_offset, out, rows, cols / 4);
+  AID_LAUNCH_CHECK("k_philox_normal");
+  return 0;
+}
+
+extern "C" int32_t aid_sample_ex(const AidScoreDims* dims, const void* packed, void* workspace,
+                                 size_t workspace_bytes, int32_t batch, int32_t n_steps,
+                                 const float* step_time_host, const int32_t* step_index_host,
+                                 const float* coef_host, int32_t T, const float* observation,
+                                 const AidSampleNoise* nz, float* z_out, float* traj_out, void* stream) {
   AID_TRY(score_dims_ok(dims));
-  if (!packed || !workspace || !z_init || !z_out || !step_time_host || !step_index_host || !coef_host)
+  if (!packed || !workspace || !nz || !z_out || !step_time_host || !step_index_host || !coef_host)
     return fail("aid_sample: null pointer");
   if (batch <= 0 || n_steps <= 0 || T <= 0) return fail("aid_sample: batch, n_steps and T must be positive");
+  if (!nz->z_init && !nz->philox) return fail("aid_sample: z_init is null and no Philox state was given");
+  const PhiloxState* philox = static_cast<const PhiloxState*>(nz->philox);
   ScoreW s;
   score_layout(dims, const_cast<void*>(packed), s);
   ScoreWS w;
@@ -829,39 +877,51 @@ extern "C" int32_t aid_sample(const AidScoreDims* dims, const void* packed, void
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   AID_CHECK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
 
-  // Per-step time arguments, evaluated on the host in fp32 exactly as the reference's tensor ops
-  // would (models/score_networks.py:121-137).  The branch is batch-global and the batch is
-  // time-constant, so it is resolved per step here without a device sync.
-  std::vector<float> sin_arg(n_steps), tn(n_steps), flag(n_steps), tw(n_steps);
+  // Per-step time arguments: the branch is batch-global and the batch is time-constant, so it is
+  // resolved per step without a device sync; tw (a by-value kernel parameter of the
+  // step's last GEMM) is evaluated on the host in fp32 exactly as the reference's tensor ops would.
+  std::vector<float> flag(n_steps), tw(n_steps);
   bool any_cont = false;
   for (int i = 0; i < n_steps; ++i) {
     const float t = step_time_host[i];
     const bool cont = (t <= 1.0f) && (t >= 0.0f);
     if (step_index_host[i] < 0 || step_index_host[i] >= T) return fail("aid_sample: step index out of range");
     if (cont) {
-      volatile float a = t * 999.0f;
-      volatile float b = 2.0f * t;
-      volatile float c = b - 1.0f;
       volatile float d = 1e-5f + t;
       volatile float e = 1.0f / d;
-      sin_arg[i] = a; tn[i] = c; flag[i] = 1.f; tw[i] = sqrtf(e);
+      flag[i] = 1.f; tw[i] = sqrtf(e);
       any_cont = true;
     } else {
-      sin_arg[i] = t; tn[i] = 0.f; flag[i] = 0.f; tw[i] = 1.f;
+      flag[i] = 0.f; tw[i] = 1.f;
     }
   }
-  AID_CHECK(cudaMemcpyAsync(w.t_sin_arg, sin_arg.data(), n_steps * 4, cudaMemcpyHostToDevice, st));
-  AID_CHECK(cudaMemcpyAsync(w.t_norm, tn.data(), n_steps * 4, cudaMemcpyHostToDevice, st));
-  AID_CHECK(cudaMemcpyAsync(w.t_flag, flag.data(), n_steps * 4, cudaMemcpyHostToDevice, st));
+  for (int base = 0; base < n_steps; base += 128) {
+    StepTimes stt;
+    const int n = n_steps - base < 128 ? n_steps - base : 128;
+    for (int i = 0; i < 128; ++i) stt.t[i] = i < n ? step_time_host[base + i] : 0.f;
+    k_step_time_args<<<1, 128, 0, st>>>(stt, n, base, w.t_sin_arg, w.t_norm, w.t_flag);
+    AID_LAUNCH_CHECK("k_step_time_args");
+  }
   AID_TRY(run_time_table(s, w, any_cont, st));
   AID_TRY(run_obs_encoder(s, w, observation, st));
 
+  const size_t zl = (size_t)batch * s.L;
+  const float* z_init = nz->z_init;
+  if (!z_init) {
+    // z_T ~ N(0, I) from the Philox stream (draw 0), written where the first step expects z
+    float* z0 = traj_out ? traj_out : z_out;
+    k_philox_normal<<<ew_grid(zl / 4), 256, 0, st>>>(philox, 0u, nz->row_offset, z0, batch, s.L / 4);
+    AID_LAUNCH_CHECK("k_philox_normal");
+    z_init = z0;
+  } else if (traj_out) {
+    AID_CHECK(cudaMemcpyAsync(traj_out, z_init, zl * 4, cudaMemcpyDeviceToDevice, st));
+  }
   const int kbl = ceil_div(s.L, TILE_K);
   k_pack_rows<<<ew_grid((size_t)w.RT * kbl * 1024), 256, 0, st>>>(z_init, batch, s.L, s.L, w.zp, w.RT, kbl, MAP_PLAIN, 0, 1);
   AID_LAUNCH_CHECK("k_pack_rows(z)");
-  const size_t zl = (size_t)batch * s.L;
-  if (traj_out) AID_CHECK(cudaMemcpyAsync(traj_out, z_init, zl * 4, cudaMemcpyDeviceToDevice, st));
 
+  // Without a trajectory buffer every step after the first updates z_out in place: a thread of the
+  // step epilogue reads its own (row, 32 columns) of z_in before it writes the same elements.
   const float* z_cur = z_init;
   int draw = 0;
   for (int i = 0; i < n_steps; ++i) {
@@ -872,7 +932,12 @@ extern "C" int32_t aid_sample(const AidScoreDims* dims, const void* packed, void
     o.tw_rows = nullptr;
     o.tw_scalar = tw[i];
     o.z_in = z_cur;
-    o.eps = (noise && ti != 0) ? noise + (size_t)(draw++) * zl : nullptr;
+    const bool noisy = ti != 0 && !nz->deterministic;
+    o.eps = (noisy && nz->noise) ? nz->noise + (size_t)draw * zl : nullptr;
+    o.philox = (noisy && !nz->noise) ? philox : nullptr;
+    o.philox_draw = 1u + (unsigned)i;
+    o.row_offset = nz->row_offset;
+    if (noisy) ++draw;
     o.c_s1 = coef_host[0 * T + ti];
     o.c_ra = coef_host[1 * T + ti];
     o.c_c1 = coef_host[2 * T + ti];
@@ -887,6 +952,23 @@ extern "C" int32_t aid_sample(const AidScoreDims* dims, const void* packed, void
   return 0;
 }
 
+extern "C" int32_t aid_sample(const AidScoreDims* dims, const void* packed, void* workspace,
+                              size_t workspace_bytes, int32_t batch, int32_t n_steps,
+                              const float* step_time_host, const int32_t* step_index_host,
+                              const float* coef_host, int32_t T, const float* observation,
+                              const float* z_init, const float* noise, float* z_out, float* traj_out,
+                              void* stream) {
+  if (!z_init) return fail("aid_sample: null pointer");
+  AidSampleNoise nz;
+  nz.z_init = z_init;
+  nz.noise = noise;
+  nz.philox = nullptr;
+  nz.row_offset = 0;
+  nz.deterministic = noise ? 0 : 1;
+  return aid_sample_ex(dims, packed, workspace, workspace_bytes, batch, n_steps, step_time_host, step_index_host,
+                       coef_host, T, observation, &nz, z_out, traj_out, stream);
+}
+
 // ------------------------------------------------------------------------------------------
 // Primitive for tests
 __global__ void k_unpack_rows(const __nv_bfloat16* __restrict__ src, int rows, int cols, int kb_total,
@@ -897,7 +979,7 @@ __global__ void k_unpack_rows(const __nv_bfloat16* __restrict__ src, int rows, i
     int row = (int)(idx / cols), c = (int)(idx % cols);
     int rt = row >> 7, r = row & 127, kb = c >> 6, cc = c & 63;
     const __nv_bfloat16* tile = src + ((size_t)rt * kb_total + kb) * TILE_ELEMS;
-    out[(size_t)row * ld + c] = __bfloat162float(tile[packed_off(r, cc)]);
+    out[(size_t)row * ld + c] = op16_to_float(tile + packed_off(r, cc));
   }
 }
 
@@ -991,7 +1073,7 @@ __global__ void k_pack_strided(const float* __restrict__ src, long long rs, long
     }
     if (want_lo) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] -= __bfloat162float(__float2bfloat16_rn(v[i]));
+      for (int i = 0; i < 8; ++i) v[i] -= op16_round(v[i]);
     }
     store_chunk(dst, rt, kb, kb_total, r, ch, v, nw);
   }
@@ -1089,6 +1171,13 @@ extern "C" int32_t aid_gemm_nt(const float* a, int64_t a_rs, int64_t a_cs, const
 
 // ------------------------------------------------------------------------------------------
 extern "C" int32_t aid_abi_version(void) { return AID_ABI_VERSION; }
+extern "C" int32_t aid_operand_type(void) {
+#ifdef AID_F16
+  return 1;
+#else
+  return 0;
+#endif
+}
 extern "C" const char* aid_last_error(void) { return g_err.c_str(); }
 extern "C" int32_t aid_device_count(void) {
   int n = 0;

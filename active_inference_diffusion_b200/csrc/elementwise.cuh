@@ -33,10 +33,10 @@ __device__ __forceinline__ void chunk_coords_rowmajor(size_t idx, int kb_total, 
 __device__ __forceinline__ void store_chunk(__nv_bfloat16* dst, int rt, int kb, int kb_total, int r,
                                             int ch, const float (&v)[8], int nw = 1) {
   uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]);
-  o.y = pack_bf16x2(v[2], v[3]);
-  o.z = pack_bf16x2(v[4], v[5]);
-  o.w = pack_bf16x2(v[6], v[7]);
+  o.x = pack_op16x2(v[0], v[1]);
+  o.y = pack_op16x2(v[2], v[3]);
+  o.z = pack_op16x2(v[4], v[5]);
+  o.w = pack_op16x2(v[6], v[7]);
   const int R = nw * TILE_M;
   __nv_bfloat16* tile = dst + ((size_t)(rt / nw) * kb_total + kb) * ((size_t)nw * TILE_ELEMS);
   *reinterpret_cast<uint4*>(tile + ch * (R * 8) + ((rt % nw) * TILE_M + r) * 8) = o;

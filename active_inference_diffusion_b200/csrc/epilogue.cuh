@@ -76,8 +76,8 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 // 8 consecutive bf16 columns (16-byte chunk `chunk`) of row r into a staged packed tile
 __device__ __forceinline__ void sts_packed8(uint32_t tile_smem, int r, int chunk, const float* y) {
-  sts_v4(tile_smem + chunk * (TILE_M * 16) + r * 16, pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-         pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+  sts_v4(tile_smem + chunk * (TILE_M * 16) + r * 16, pack_op16x2(y[0], y[1]), pack_op16x2(y[2], y[3]),
+         pack_op16x2(y[4], y[5]), pack_op16x2(y[6], y[7]));
 }
 
 // Packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE-rn fp32 results per issue slot).
@@ -417,10 +417,10 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
           sts_packed8(stg.base, r, c, y);
         } else {
           uint4 v;
-          v.x = pack_bf16x2(y[0], y[1]);
-          v.y = pack_bf16x2(y[2], y[3]);
-          v.z = pack_bf16x2(y[4], y[5]);
-          v.w = pack_bf16x2(y[6], y[7]);
+          v.x = pack_op16x2(y[0], y[1]);
+          v.y = pack_op16x2(y[2], y[3]);
+          v.z = pack_op16x2(y[4], y[5]);
+          v.w = pack_op16x2(y[6], y[7]);
           *reinterpret_cast<uint4*>(tile + c * (TILE_M * 8) + r * 8) = v;
         }
       }
@@ -445,6 +445,9 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
     uint32_t raw[32];
     const float mult = __ldg(e.out_mult);
     const float tw = e.tw_rows ? ((row < e.rows_valid) ? __ldg(e.tw_rows + row) : 0.f) : e.tw_scalar;
+    PhiloxState ps{0ull, 0ull};
+    if (e.philox) ps = *e.philox;
+    const bool has_eps = e.eps != nullptr || e.philox != nullptr;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       const int n0 = nt * TILE_N + c * 32;
@@ -461,6 +464,8 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
         if (e.do_step && live && (col + 3 < e.n_valid)) {
           zv[q] = *reinterpret_cast<const float4*>(e.z_in + (size_t)row * e.n_valid + col);
           if (e.eps) ev[q] = *reinterpret_cast<const float4*>(e.eps + (size_t)row * e.n_valid + col);
+          else if (e.philox)
+            ev[q] = philox_normal4(ps, e.philox_draw, (unsigned long long)(e.row_offset + row), (uint32_t)(col >> 2));
         }
       }
       tmem_ld_wait();
@@ -483,7 +488,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
             // (z + s1*score) * ra ; c1*pred + c2*z ; + sigma*eps   (rounding order of the reference)
             float pred = __fmul_rn(__fadd_rn(zz[i], __fmul_rn(e.c_s1, y[q * 4 + i])), e.c_ra);
             float mu = __fadd_rn(__fmul_rn(e.c_c1, pred), __fmul_rn(e.c_c2, zz[i]));
-            if (e.eps) mu = __fadd_rn(mu, __fmul_rn(e.c_sigma, ee[i]));
+            if (has_eps) mu = __fadd_rn(mu, __fmul_rn(e.c_sigma, ee[i]));
             y[q * 4 + i] = ok ? mu : 0.f;
           }
           if (ok)

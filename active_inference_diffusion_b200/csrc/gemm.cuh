@@ -23,7 +23,9 @@
 // warp2 = TMEM allocator, warps 4..11 = two epilogue groups (tile sequence number parity).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "ptx.cuh"
+#include "philox.cuh"
 
 namespace aid {
 
@@ -111,7 +113,10 @@ struct EpiArgs {
   float tw_scalar;           // used when tw_rows == null
   int do_step;               // 0: write score; 1: reverse-diffusion update
   const float* z_in;         // [rows_valid, n_valid] row-major
-  const float* eps;          // [rows_valid, n_valid] or null (deterministic / t == 0)
+  const float* eps;          // [rows_valid, n_valid] or null (deterministic / t == 0 / Philox mode)
+  const PhiloxState* philox; // device {seed, call offset}: draw eps in the epilogue (no noise tensor), or null
+  unsigned int philox_draw;  // draw index of this step (philox.cuh)
+  long long row_offset;      // global index of row 0 (sharded batches draw the unsharded stream)
   float c_s1, c_ra, c_c1, c_c2, c_sigma;
   float* z_out;              // row-major fp32 (score or new z)
 };
@@ -203,9 +208,38 @@ __device__ __forceinline__ void act_apply32(float (&y)[32], int act) {
   }
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+// Tensor-core operand element type, fixed per build of the library:
+//   default     : bf16 (8-bit significand)  -> libaid_sm100.so      ("bf16" precision)
+//   -DAID_F16   : IEEE fp16 (11-bit significand, the TF32 significand) -> libaid_sm100_f16.so ("f16")
+// Both are kind::f16 UMMAs at the same tensor-pipe rate with fp32 accumulation; fp16 operands give
+// TF32-class products (rounding 2^-11 instead of 2^-8) and are what meets the rel-1e-3 contract.
+// fp16 has a 5-bit exponent: conversions saturate to +-65504 instead of producing inf, activations
+// are LayerNorm-scaled, and the training path scales its cotangent streams (train.inc).
+// pack_op16x2(a, b): a in the low half, b in the high half, round to nearest even.
+__device__ __forceinline__ uint32_t pack_op16x2(float a, float b) {
+#ifdef AID_F16
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+#else
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+#endif
+}
+// value of x after rounding to the operand type (hi part of the x3 split) and one stored element back to fp32
+__device__ __forceinline__ float op16_round(float x) {
+#ifdef AID_F16
+  return __half2float(__float2half_rn(x));
+#else
+  return __bfloat162float(__float2bfloat16_rn(x));
+#endif
+}
+__device__ __forceinline__ float op16_to_float(const __nv_bfloat16* p) {
+#ifdef AID_F16
+  return __half2float(*reinterpret_cast<const __half*>(p));
+#else
+  return __bfloat162float(*p);
+#endif
 }
 
 // Write 32 consecutive columns [c0, c0+32) of row r (c0 % 32 == 0) into a packed tile row.
@@ -214,10 +248,10 @@ __device__ __forceinline__ void store_packed32(__nv_bfloat16* tile_base, int r, 
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint4 v;
-    v.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
-    v.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
-    v.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
-    v.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
+    v.x = pack_op16x2(y[q * 8 + 0], y[q * 8 + 1]);
+    v.y = pack_op16x2(y[q * 8 + 2], y[q * 8 + 3]);
+    v.z = pack_op16x2(y[q * 8 + 4], y[q * 8 + 5]);
+    v.w = pack_op16x2(y[q * 8 + 6], y[q * 8 + 7]);
     int chunk = (c0_in_tile >> 3) + q;
     *reinterpret_cast<uint4*>(tile_base + chunk * (TILE_M * 8) + r * 8) = v;
   }

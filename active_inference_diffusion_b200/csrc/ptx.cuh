@@ -213,9 +213,21 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_
 }
 // Instruction descriptor: D=f32 (bits 4-5 =1), A=B=bf16 (bits 7-9, 10-12 =1), both K-major,
 // N>>3 at bit 17, M>>4 at bit 24.
+// A/B format field: 1 = bf16, 0 = fp16 (-DAID_F16 builds, see pack_op16x2 in gemm.cuh).
+// MN-major operands (bits 15 / 16) are selected by umma_idesc_op16_mn below.
+#ifdef AID_F16
+constexpr uint32_t UMMA_OP16_FMT = 0u;
+#else
+constexpr uint32_t UMMA_OP16_FMT = 1u;
+#endif
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+  return (1u << 4) | (UMMA_OP16_FMT << 7) | (UMMA_OP16_FMT << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+// same with both operands MN-major (transpose bits 15 = A, 16 = B): the weight-gradient GEMM reads
+// the row-major operand packs along their row (= reduction) dimension
+__host__ __device__ constexpr uint32_t umma_idesc_op16_mn(int M, int N) {
+  return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
 }
 
 }  // namespace aid

@@ -120,31 +120,133 @@ class LatentDiffusionProcess(nn.Module):
         return a * z_start + b * noise, noise
 
     # ---- reverse process --------------------------------------------------------------------
-    def _run_sampler(self, score_network, observation: Optional[torch.Tensor], z_init: torch.Tensor,
-                     step_times: List[float], step_index: List[int], noise: Optional[torch.Tensor],
-                     return_trajectory: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-        dev = _lib.require_cuda(z_init, observation, noise)
-        z_init, observation, noise = _lib.f32c(z_init), _lib.f32c(observation), _lib.f32c(noise)
-        batch, n_steps = z_init.shape[0], len(step_times)
-        if batch == 0:                  # empty batch: T+1 empty latents, as the reference's loop gives
-            traj = z_init.new_empty(n_steps + 1, 0, self.latent_dim) if return_trajectory else None
-            return torch.empty_like(z_init), traj
+    # Noise source of draws that are not injected: "torch" draws z_T and the per-step noise with
+    # torch.randn in the reference's order (core/diffusion.py:190,236) and hands the tensors to the
+    # library; "philox" lets the kernels draw them (csrc/philox.cuh: no [T-1,B,L] tensor in HBM, and
+    # a row's stream depends only on (seed, call, global row), so sharded batches agree with the
+    # unsharded one).  The Philox seed is taken from torch's CUDA generator at first use, so
+    # torch.manual_seed still fixes the run.
+    noise_source = "torch"
+    # CUDA-graph replay of the whole sampler call (2,350 launches at T=50): "auto" = batches of at
+    # most `graph_max_batch` rows without a returned trajectory (launch-latency-bound regime), True,
+    # or False.
+    use_graph = "auto"
+    graph_max_batch = 16384
+    row_offset = 0            # global index of this rank's first row (Philox stream of sharded batches)
+
+    def philox_state(self, device: torch.device) -> torch.Tensor:
+        """Device tensor [seed, call offset] (int64) of the in-kernel noise stream."""
+        states = self.__dict__.setdefault("_philox_states", {})
+        st = states.get(device)
+        if st is None:
+            st = torch.zeros(2, dtype=torch.int64, device=device)
+            st[0] = torch.randint(0, 2 ** 62, (1,), device=device, dtype=torch.int64)[0]
+            states[device] = st
+        return st
+
+    def seed_philox(self, seed: int, device: torch.device) -> None:
+        st = self.philox_state(device)
+        st.copy_(torch.tensor([int(seed), 0], dtype=torch.int64))
+
+    def _launch_sampler(self, score_network, packed, ws, observation, z_init, noise, philox, deterministic,
+                        step_times, step_index, z_out, traj) -> None:
+        dev = z_out.device
+        batch, n_steps = z_out.shape[0], len(step_times)
         T = int(self.betas.shape[0])
         coef = self.reverse_coefficients()
-        packed = score_network.packed_weights()
-        ws = score_network.workspace(batch, max(n_steps, 1), dev)
         d = score_network.dims()
-        z_out = torch.empty_like(z_init)
-        traj = torch.empty(n_steps + 1, batch, self.latent_dim, dtype=torch.float32, device=dev) \
-            if return_trajectory else None
         times = (ctypes.c_float * n_steps)(*step_times)
         index = (ctypes.c_int32 * n_steps)(*step_index)
-        _lib.check(_lib.lib().aid_sample(
-            ctypes.byref(d), packed.data_ptr(), ws.data_ptr(), ws.numel(), batch, n_steps, times, index,
-            coef.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), T, _lib.ptr(observation),
-            z_init.data_ptr(), _lib.ptr(noise), z_out.data_ptr(), _lib.ptr(traj), _lib.stream_ptr(dev)),
-            "aid_sample")
+        nz = _lib.AidSampleNoise(_lib.ptr(z_init), _lib.ptr(noise), _lib.ptr(philox), int(self.row_offset),
+                                 int(bool(deterministic)))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().aid_sample_ex(
+                ctypes.byref(d), packed.data_ptr(), ws.data_ptr(), ws.numel(), batch, n_steps, times, index,
+                coef.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), T, _lib.ptr(observation), ctypes.byref(nz),
+                z_out.data_ptr(), _lib.ptr(traj), _lib.stream_ptr(dev)), "aid_sample_ex")
+
+    def _run_sampler(self, score_network, observation: Optional[torch.Tensor], z_init: Optional[torch.Tensor],
+                     step_times: List[float], step_index: List[int], noise: Optional[torch.Tensor],
+                     return_trajectory: bool, *, batch: Optional[int] = None, deterministic: bool = False,
+                     philox: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """One library call for the whole loop.  `z_init` / `noise` are injected draws; whatever is
+        missing (and needed) comes from the in-kernel Philox stream when `philox` is set."""
+        dev = _lib.require_cuda(z_init, observation, noise, next(score_network.parameters()))
+        z_init, observation, noise = _lib.f32c(z_init), _lib.f32c(observation), _lib.f32c(noise)
+        batch = int(z_init.shape[0] if z_init is not None else batch)
+        n_steps = len(step_times)
+        if batch == 0:                  # empty batch: T+1 empty latents, as the reference's loop gives
+            z = torch.empty(0, self.latent_dim, dtype=torch.float32, device=dev)
+            traj = z.new_empty(n_steps + 1, 0, self.latent_dim) if return_trajectory else None
+            return z, traj
+        if z_init is None and not philox:
+            raise ValueError("_run_sampler: z_init is required unless the Philox stream is used")
+        packed = score_network.packed_weights()
+        ws = score_network.workspace(batch, max(n_steps, 1), dev)
+        state = None
+        if philox:
+            state = self.philox_state(dev)
+        graphed = self.use_graph is True or (self.use_graph == "auto" and batch <= self.graph_max_batch)
+        if graphed and not return_trajectory and not torch.cuda.is_current_stream_capturing():
+            return self._run_sampler_graphed(score_network, packed, observation, z_init, noise, state,
+                                             deterministic, step_times, step_index, batch, dev), None
+        if state is not None:
+            state[1] += 1               # a new call of the stream (device-side, no host sync)
+        z_out = torch.empty(batch, self.latent_dim, dtype=torch.float32, device=dev)
+        traj = torch.empty(n_steps + 1, batch, self.latent_dim, dtype=torch.float32, device=dev) \
+            if return_trajectory else None
+        self._launch_sampler(score_network, packed, ws, observation, z_init, noise, state, deterministic,
+                             step_times, step_index, z_out, traj)
         return z_out, traj
+
+    def _run_sampler_graphed(self, score_network, packed, observation, z_init, noise, state, deterministic,
+                             step_times, step_index, batch, dev) -> torch.Tensor:
+        """Capture the call once per (shape, schedule, weights buffer) and replay it: the host enqueues
+        ONE graph launch instead of ~47 kernels per denoise step.  Inputs are copied into the graph's
+        static buffers; the Philox call offset is advanced inside the graph, so every replay draws
+        fresh noise."""
+        graphs = self.__dict__.setdefault("_sampler_graphs", {})
+        key = (dev, _lib.operand_type(), batch, tuple(step_times), tuple(step_index), observation is None,
+               z_init is None, noise is None, state is None, bool(deterministic), int(self.row_offset),
+               score_network.dims().obs_dim)
+        g = graphs.get(key)
+        if g is not None and g["packed_ptr"] != packed.data_ptr():
+            g = None                    # the weights were re-packed into a new buffer
+        if g is None:
+            L = self.latent_dim
+            g = {"packed_ptr": packed.data_ptr(), "packed": packed,
+                 "obs": None if observation is None else torch.empty_like(observation),
+                 "z_init": None if z_init is None else torch.empty_like(z_init),
+                 "noise": None if noise is None else torch.empty_like(noise),
+                 "z_out": torch.empty(batch, L, dtype=torch.float32, device=dev),
+                 "ws": torch.empty(score_network.workspace(batch, max(len(step_times), 1), dev).numel(),
+                                   dtype=torch.uint8, device=dev)}
+            for name, src in (("obs", observation), ("z_init", z_init), ("noise", noise)):
+                if src is not None:
+                    g[name].copy_(src)
+
+            def body():
+                if state is not None:
+                    state[1] += 1
+                self._launch_sampler(score_network, packed, g["ws"], g["obs"], g["z_init"], g["noise"], state,
+                                     deterministic, step_times, step_index, g["z_out"], None)
+
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                body()                  # warm-up: one-time kernel attribute setup happens outside the capture
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g["graph"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g["graph"]):
+                body()
+            if len(graphs) >= 8:        # bounded cache: drop the oldest shape
+                graphs.pop(next(iter(graphs)))
+            graphs[key] = g
+        for name, src in (("obs", observation), ("z_init", z_init), ("noise", noise)):
+            if src is not None:
+                g[name].copy_(src, non_blocking=True)
+        g["graph"].replay()
+        return g["z_out"].clone()
 
     def generate_latent_trajectory(self, score_network: nn.Module, batch_size: int,
                                    observation: Optional[torch.Tensor] = None,
@@ -161,17 +263,19 @@ class LatentDiffusionProcess(nn.Module):
         if observation is not None:
             observation = observation.to(device)
         T = int(self.config.num_diffusion_steps)
-        if z_init is None:
+        philox = self.noise_source == "philox"
+        if z_init is None and not philox:
             z_init = torch.randn(batch_size, self.latent_dim, device=device)
-        if noise is None and not deterministic and T > 1:
+        if noise is None and not deterministic and T > 1 and not philox:
             noise = torch.randn(T - 1, batch_size, self.latent_dim, device=device)
         if deterministic:
             noise = None
         steps = list(reversed(range(T)))
         z, traj = self._run_sampler(score_network, observation, z_init, [float(t) for t in steps], steps,
-                                    noise, return_trajectory)
+                                    noise, return_trajectory, batch=batch_size, deterministic=deterministic,
+                                    philox=philox)
         if traj is None:
-            return [z_init, z]
+            return [z_init if z_init is not None else z.new_zeros(0), z]
         return list(traj.unbind(0))
 
     def collector_sample(self, score_network: nn.Module, observation: torch.Tensor, max_diffusion_steps: int,
@@ -185,14 +289,16 @@ class LatentDiffusionProcess(nn.Module):
         T = int(self.config.num_diffusion_steps)
         n = min(int(max_diffusion_steps), T)
         max_index = T - 1
-        if z_init is None:
+        philox = self.noise_source == "philox"
+        if z_init is None and not philox:
             z_init = torch.randn(batch, self.latent_dim, device=device)
-        if noise is None and n > 1:
+        if noise is None and n > 1 and not philox:
             noise = torch.randn(n - 1, batch, self.latent_dim, device=device)
         steps = list(reversed(range(n)))
         # torch.full(..., step / max_index) stores the python double as fp32
         times = [float(np.float32(s / max_index)) if max_index > 0 else 0.0 for s in steps]
-        z, _ = self._run_sampler(score_network, observation, z_init, times, steps, noise, False)
+        z, _ = self._run_sampler(score_network, observation, z_init, times, steps, noise, False, batch=batch,
+                                 philox=philox)
         return z
 
     def p_sample(self, z_t: torch.Tensor, t: torch.Tensor, score: torch.Tensor,

@@ -164,9 +164,7 @@ class HeadsBundle:
         self.policy, self.dynamics, self.value, self.reward = policy, dynamics, value, reward
         for m in (policy, dynamics, value):
             object.__setattr__(m, "_owner", self)
-        self._packed: Optional[torch.Tensor] = None
-        self._key = None
-        self._ws: Optional[torch.Tensor] = None
+        self._cache = _lib.PackedCache()
 
     def dims(self) -> _lib.AidHeadsDims:
         return _lib.AidHeadsDims(self.policy.latent_dim, self.policy.action_dim, self.policy.hidden_dim,
@@ -180,32 +178,35 @@ class HeadsBundle:
             out += [named[k] for k in keys]
         return out
 
-    def packed_weights(self) -> torch.Tensor:
+    def invalidate_packed(self) -> None:
+        """Required after in-place `.data` edits of head parameters (see _lib.PackedCache)."""
+        self._cache.invalidate()
+
+    def packed_weights(self, verify: bool = False) -> torch.Tensor:
         params = self._params()
         dev = _lib.require_cuda(*params)
-        key = tuple((p.data_ptr(), p._version) for p in params)
-        if self._packed is not None and self._key == key and self._packed.device == dev:
-            return self._packed
-        l, d = _lib.lib(), self.dims()
-        nbytes = l.aid_heads_packed_bytes(ctypes.byref(d))
-        if nbytes == 0:
-            _lib.check(-1, "aid_heads_packed_bytes")
-        keep = [_lib.f32c(p.detach()) for p in params]
-        table = (ctypes.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
-        packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.check(l.aid_heads_pack(ctypes.byref(d), table, len(keep), packed.data_ptr(), nbytes,
-                                    _lib.stream_ptr(dev)), "aid_heads_pack")
-        self._packed, self._key = packed, key
-        return packed
+
+        def build():
+            l, d = _lib.lib(), self.dims()
+            nbytes = l.aid_heads_packed_bytes(ctypes.byref(d))
+            if nbytes == 0:
+                _lib.check(-1, "aid_heads_packed_bytes")
+            keep = [_lib.f32c(p.detach()) for p in params]
+            table = (ctypes.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(l.aid_heads_pack(ctypes.byref(d), table, len(keep), packed.data_ptr(), nbytes,
+                                            _lib.stream_ptr(dev)), "aid_heads_pack")
+            return packed
+
+        return self._cache.get(("heads", _lib.operand_type()), params, build, verify)
 
     def workspace(self, batch: int, device: torch.device) -> torch.Tensor:
         l, d = _lib.lib(), self.dims()
         need = l.aid_heads_workspace_bytes(ctypes.byref(d), batch)
         if need == 0:
             _lib.check(-1, "aid_heads_workspace_bytes")
-        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
-        return self._ws
+        return self._cache.workspace(need, device)
 
     def head_forward(self, which: int, z: torch.Tensor, aux: Optional[torch.Tensor] = None) -> torch.Tensor:
         dev = _lib.require_cuda(z, aux)
@@ -217,9 +218,10 @@ class HeadsBundle:
         if B == 0:                      # empty batch: empty result, as the reference's modules give
             return out
         packed, ws = self.packed_weights(), self.workspace(B, dev)
-        _lib.check(_lib.lib().aid_head_forward(ctypes.byref(d), packed.data_ptr(), ws.data_ptr(), ws.numel(), which,
-                                               B, z.data_ptr(), _lib.ptr(aux), out.data_ptr(), _lib.stream_ptr(dev)),
-                   "aid_head_forward")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().aid_head_forward(ctypes.byref(d), packed.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                   which, B, z.data_ptr(), _lib.ptr(aux), out.data_ptr(),
+                                                   _lib.stream_ptr(dev)), "aid_head_forward")
         return out
 
     def efe_rollout(self, latent: torch.Tensor, horizon: int, num_trajectories: int, cfg: Dict[str, float],
@@ -245,9 +247,10 @@ class HeadsBundle:
         c = _lib.AidEfeConfig(cfg["epistemic_weight"], cfg["pragmatic_weight"], cfg["consistency_weight"],
                               cfg["discount_factor"])
         packed, ws = self.packed_weights(), self.workspace(B, dev)
-        _lib.check(_lib.lib().aid_efe_rollout(
-            ctypes.byref(d), packed.data_ptr(), ws.data_ptr(), ws.numel(), B, h, K, ctypes.byref(c),
-            tau.data_ptr(), latent.data_ptr(), policy_noise.data_ptr(), reparam_noise.data_ptr(),
-            _lib.ptr(epistemic), efe.data_ptr(), first.data_ptr(), prag.data_ptr(), cons.data_ptr(),
-            _lib.stream_ptr(dev)), "aid_efe_rollout")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().aid_efe_rollout(
+                ctypes.byref(d), packed.data_ptr(), ws.data_ptr(), ws.numel(), B, h, K, ctypes.byref(c),
+                tau.data_ptr(), latent.data_ptr(), policy_noise.data_ptr(), reparam_noise.data_ptr(),
+                _lib.ptr(epistemic), efe.data_ptr(), first.data_ptr(), prag.data_ptr(), cons.data_ptr(),
+                _lib.stream_ptr(dev)), "aid_efe_rollout")
         return efe, first, prag, cons

@@ -18,6 +18,7 @@ from .diffusion import LatentDiffusionProcess
 from .heads import (DiffusionConditionedPolicy, HeadsBundle, LatentDynamicsModel, ValueNetwork,
                     make_reward_predictor)
 from .score_network import LatentScoreNetwork
+from . import _lib
 
 
 class CandidateScorer(nn.Module):
@@ -35,29 +36,90 @@ class CandidateScorer(nn.Module):
         self.latent_dynamics = LatentDynamicsModel(L, action_dim, H, num_layers=3)
         self.reward_predictor = make_reward_predictor(L, H)
         self.heads = HeadsBundle(self.policy_network, self.latent_dynamics, self.value_network, self.reward_predictor)
+        self.latent_diffusion.noise_source = "philox"     # in-kernel noise: no [T-1,B,L] tensor in HBM
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "heads"):
+            self.heads.invalidate_packed()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_packed()
+        return out
+
+    def invalidate_packed(self) -> None:
+        """Drop the derived packed-weight caches (needed after in-place `.data` edits)."""
+        self.latent_score_network.invalidate_packed()
+        self.heads.invalidate_packed()
 
     def efe_config(self) -> Dict[str, float]:
         c = self.config
         return {"epistemic_weight": float(c.epistemic_weight), "pragmatic_weight": float(c.pragmatic_weight),
                 "consistency_weight": float(c.consistency_weight), "discount_factor": float(c.discount_factor)}
 
-    @torch.no_grad()
-    def forward(self, observation: torch.Tensor, horizon: Optional[int] = None, num_trajectories: int = 1,
-                epistemic: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """observation [B,O] (device) -> (efe [B], first_action [B,A], latent [B,L]).
-        All noise (z_T, T-1 step noises, policy and reparameterisation draws) is drawn here on the
-        device, one stream of standard normals per candidate row."""
-        h = int(horizon or self.config.efe_horizon)
+    # Whole-call CUDA graph (sampler + noise draws + EFE rollout, ~2,900 launches at T=50, K=1, h=5) for
+    # batches in the launch-latency-bound regime: "auto" = at most `graph_max_batch` rows.
+    use_graph = "auto"
+    graph_max_batch = 16384
+
+    def _score(self, observation: torch.Tensor, h: int, K: int, epistemic: Optional[torch.Tensor]):
         B, dev = observation.shape[0], observation.device
         traj = self.latent_diffusion.generate_latent_trajectory(
             self.latent_score_network, B, observation, deterministic=False, return_trajectory=False)
         latent = traj[-1]
-        K = int(num_trajectories)
         policy_noise = torch.randn(K * h, B, self.action_dim, device=dev)
         reparam_noise = torch.randn(K * h, B, self.latent_dim, device=dev)
         efe, first_action, _, _ = self.heads.efe_rollout(latent, h, K, self.efe_config(), self.preference_temperature,
                                                          policy_noise, reparam_noise, epistemic)
         return efe, first_action, latent
+
+    @torch.no_grad()
+    def forward(self, observation: torch.Tensor, horizon: Optional[int] = None, num_trajectories: int = 1,
+                epistemic: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """observation [B,O] (device) -> (efe [B], first_action [B,A], latent [B,L]).
+        All noise is drawn on the device, one stream of standard normals per candidate row: z_T and
+        the T-1 step noises inside the sampler kernels (`latent_diffusion.noise_source == "philox"`,
+        the default here) and the policy / reparameterisation draws by torch."""
+        h = int(horizon or self.config.efe_horizon)
+        K = int(num_trajectories)
+        B, dev = observation.shape[0], observation.device
+        graphed = self.use_graph is True or (self.use_graph == "auto" and 0 < B <= self.graph_max_batch)
+        if not graphed or torch.cuda.is_current_stream_capturing():
+            return self._score(observation, h, K, epistemic)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        packed = (self.latent_score_network.packed_weights().data_ptr(), self.heads.packed_weights().data_ptr())
+        key = (dev, _lib.operand_type(), tuple(observation.shape), h, K, epistemic is None,
+               self.latent_diffusion.noise_source, int(self.latent_diffusion.row_offset))
+        g = graphs.get(key)
+        if g is not None and g["packed"] != packed:
+            g = None                    # weights were re-packed into new buffers: capture again
+        if g is None:
+            g = {"packed": packed, "obs": observation.clone(),
+                 "epi": None if epistemic is None else epistemic.clone()}
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            prev = self.latent_diffusion.use_graph
+            self.latent_diffusion.use_graph = False          # the sampler is captured as part of THIS graph
+            try:
+                with torch.cuda.stream(side):
+                    self._score(g["obs"], h, K, g["epi"])    # warm-up outside the capture
+                torch.cuda.current_stream(dev).wait_stream(side)
+                g["graph"] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g["graph"]):
+                    g["out"] = self._score(g["obs"], h, K, g["epi"])
+            finally:
+                self.latent_diffusion.use_graph = prev
+            if len(graphs) >= 8:
+                graphs.pop(next(iter(graphs)))
+            graphs[key] = g
+        g["obs"].copy_(observation, non_blocking=True)
+        if epistemic is not None:
+            g["epi"].copy_(epistemic, non_blocking=True)
+        g["graph"].replay()
+        efe, first_action, latent = g["out"]
+        return efe.clone(), first_action.clone(), latent.clone()
 
     @torch.no_grad()
     def forward_pixels(self, encoder: nn.Module, pixels: torch.Tensor, **kw

@@ -99,9 +99,7 @@ class LatentScoreNetwork(nn.Module):
         self.output_multiplier = nn.Parameter(torch.ones(1) * output_scale)
         nn.init.zeros_(self.output_proj[-1].weight)
         # derived caches (not part of the state_dict)
-        self._packed: Optional[torch.Tensor] = None
-        self._packed_key = None
-        self._ws: Optional[torch.Tensor] = None
+        object.__setattr__(self, "_cache", _lib.PackedCache())
 
     # ---- derived cache -------------------------------------------------------------------
     @property
@@ -119,25 +117,42 @@ class LatentScoreNetwork(nn.Module):
             keys += [f"transformer_blocks.{i}.{k}" for k in _lib.SCORE_BLOCK_KEYS]
         return [named[k] for k in keys]
 
-    def packed_weights(self) -> torch.Tensor:
-        """bf16 tcgen05 operand tiles of the current parameters (rebuilt when they change)."""
+    def invalidate_packed(self) -> None:
+        """Drop the packed operand tiles: required after in-place edits of parameters through `.data`
+        (they do not bump the version counters the cache is keyed on; see _lib.PackedCache)."""
+        self._cache.invalidate()
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._cache.invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._cache.invalidate()
+        return out
+
+    def packed_weights(self, verify: bool = False) -> torch.Tensor:
+        """tcgen05 operand tiles of the current parameters in the current operand type
+        (`_lib.operand_type()`), rebuilt when the parameters change."""
         params = self._param_table()
         dev = _lib.require_cuda(*params)
-        key = tuple((p.data_ptr(), p._version) for p in params)
-        if self._packed is not None and self._packed_key == key and self._packed.device == dev:
-            return self._packed
-        l = _lib.lib()
-        d = self.dims()
-        nbytes = l.aid_score_packed_bytes(ctypes.byref(d))
-        if nbytes == 0:
-            _lib.check(-1, "aid_score_packed_bytes")
-        keep = [_lib.f32c(p.detach()) for p in params]
-        table = (ctypes.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
-        packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.check(l.aid_score_pack(ctypes.byref(d), table, len(keep), packed.data_ptr(), nbytes,
-                                    _lib.stream_ptr(dev)), "aid_score_pack")
-        self._packed, self._packed_key = packed, key
-        return packed
+
+        def build():
+            l = _lib.lib()
+            d = self.dims()
+            nbytes = l.aid_score_packed_bytes(ctypes.byref(d))
+            if nbytes == 0:
+                _lib.check(-1, "aid_score_packed_bytes")
+            keep = [_lib.f32c(p.detach()) for p in params]
+            table = (ctypes.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(l.aid_score_pack(ctypes.byref(d), table, len(keep), packed.data_ptr(), nbytes,
+                                            _lib.stream_ptr(dev)), "aid_score_pack")
+            return packed
+
+        return self._cache.get(("score", _lib.operand_type()), params, build, verify)
 
     def workspace(self, batch: int, table_rows: int, device: torch.device) -> torch.Tensor:
         l = _lib.lib()
@@ -145,9 +160,7 @@ class LatentScoreNetwork(nn.Module):
         need = l.aid_score_workspace_bytes(ctypes.byref(d), batch, table_rows)
         if need == 0:
             _lib.check(-1, "aid_score_workspace_bytes")
-        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
-        return self._ws
+        return self._cache.workspace(need, device)
 
     # ---- forward -------------------------------------------------------------------------
     def forward(self, z_t: torch.Tensor, time: torch.Tensor,
@@ -182,8 +195,9 @@ class LatentScoreNetwork(nn.Module):
         ws = self.workspace(batch, batch, dev)
         out = torch.empty(batch, self.latent_dim, dtype=torch.float32, device=dev)
         d = self.dims()
-        _lib.check(_lib.lib().aid_score_forward(
-            ctypes.byref(d), packed.data_ptr(), ws.data_ptr(), ws.numel(), z_t.data_ptr(), time.data_ptr(),
-            _lib.ptr(observation), batch, int(continuous), out.data_ptr(), _lib.stream_ptr(dev)),
-            "aid_score_forward")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().aid_score_forward(
+                ctypes.byref(d), packed.data_ptr(), ws.data_ptr(), ws.numel(), z_t.data_ptr(), time.data_ptr(),
+                _lib.ptr(observation), batch, int(continuous), out.data_ptr(), _lib.stream_ptr(dev)),
+                "aid_score_forward")
         return out

@@ -88,9 +88,7 @@ class DrQV2Encoder(nn.Module):
             nn.Linear(self.conv_out_dim, feature_dim * 2), nn.LayerNorm(feature_dim * 2), nn.Mish(),
             nn.Dropout(0.1), nn.Linear(feature_dim * 2, feature_dim), nn.LayerNorm(feature_dim), nn.Tanh())
         self._initialize_weights()
-        self._packed: Optional[torch.Tensor] = None
-        self._packed_key = None
-        self._ws: Optional[torch.Tensor] = None
+        object.__setattr__(self, "_cache", _lib.PackedCache())
         self.precision = "bf16"
 
     def _initialize_weights(self) -> None:
@@ -113,7 +111,25 @@ class DrQV2Encoder(nn.Module):
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
         return _lib.AidEncoderDims(self.input_channels, self.obs_shape[1], self.obs_shape[2], self.num_filters,
                                    self.num_layers, self.feature_dim, int(self.use_attention),
-                                   _lib.PRECISIONS[self.precision])
+                                   _lib.PRECISIONS[self.precision][1])
+
+    def _lib_handle(self):
+        """The encoder's own `precision` names the library (operand type) and the hi/lo split."""
+        return _lib.lib(_lib.PRECISIONS[self.precision][0])
+
+    def invalidate_packed(self) -> None:
+        """Required after in-place `.data` edits of encoder parameters (see _lib.PackedCache)."""
+        self._cache.invalidate()
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._cache.invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._cache.invalidate()
+        return out
 
     def _param_table(self):
         sd = dict(self.named_parameters())
@@ -135,24 +151,25 @@ class DrQV2Encoder(nn.Module):
             table += [sd[f"output_layers.{j}.weight"], sd[f"output_layers.{j}.bias"]]
         return table
 
-    def packed_weights(self) -> torch.Tensor:
+    def packed_weights(self, verify: bool = False) -> torch.Tensor:
         params = self._param_table()
         dev = _lib.require_cuda(*params)
-        key = (self.precision,) + tuple((p.data_ptr(), p._version) for p in params if p is not None)
-        if self._packed is not None and self._packed_key == key and self._packed.device == dev:
-            return self._packed
-        l = _lib.lib()
-        d = self.dims()
-        nbytes = l.aid_encoder_packed_bytes(ctypes.byref(d))
-        if nbytes == 0:
-            _lib.check(-1, "aid_encoder_packed_bytes")
-        keep = [None if p is None else _lib.f32c(p.detach()) for p in params]
-        table = (ctypes.c_void_p * len(keep))(*[None if t is None else t.data_ptr() for t in keep])
-        packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.check(l.aid_encoder_pack(ctypes.byref(d), table, len(keep), packed.data_ptr(), nbytes,
-                                      _lib.stream_ptr(dev)), "aid_encoder_pack")
-        self._packed, self._packed_key = packed, key
-        return packed
+
+        def build():
+            l = self._lib_handle()
+            d = self.dims()
+            nbytes = l.aid_encoder_packed_bytes(ctypes.byref(d))
+            if nbytes == 0:
+                _lib.check(-1, "aid_encoder_packed_bytes", l)
+            keep = [None if p is None else _lib.f32c(p.detach()) for p in params]
+            table = (ctypes.c_void_p * len(keep))(*[None if t is None else t.data_ptr() for t in keep])
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(l.aid_encoder_pack(ctypes.byref(d), table, len(keep), packed.data_ptr(), nbytes,
+                                              _lib.stream_ptr(dev)), "aid_encoder_pack", l)
+            return packed
+
+        return self._cache.get(("encoder", self.precision), params, build, verify)
 
     def _canonical_input(self, x: torch.Tensor) -> torch.Tensor:
         # input conventions of visual_encoders.py:149-162
@@ -190,7 +207,7 @@ class DrQV2Encoder(nn.Module):
             pooled = torch.cat([x.mean(dim=1, keepdim=True), x.max(dim=1, keepdim=True)[0]], dim=1)
             x = x + x * torch.sigmoid(att.spatial_conv(pooled) / att.temperature)
         x = self.ln(x.reshape(x.shape[0], -1))
-        with autograd_path.precision("bf16x3" if self.precision == "bf16x3" else "bf16"):
+        with autograd_path.precision(self.precision):
             return autograd_path.seq(self.output_layers, x)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -201,16 +218,16 @@ class DrQV2Encoder(nn.Module):
         is_u8 = x.dtype == torch.uint8
         x = x.contiguous() if is_u8 else _lib.f32c(x)
         packed = self.packed_weights()
-        l = _lib.lib()
+        l = self._lib_handle()
         d = self.dims()
         batch = x.shape[0]
         need = l.aid_encoder_workspace_bytes(ctypes.byref(d), batch)
         if need == 0:
-            _lib.check(-1, "aid_encoder_workspace_bytes")
-        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            _lib.check(-1, "aid_encoder_workspace_bytes", l)
+        ws = self._cache.workspace(need, dev)
         out = torch.empty(batch, self.feature_dim, dtype=torch.float32, device=dev)
-        _lib.check(l.aid_encoder_forward(ctypes.byref(d), packed.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
-                                         batch, x.data_ptr(), int(is_u8), out.data_ptr(), _lib.stream_ptr(dev)),
-                   "aid_encoder_forward")
+        with torch.cuda.device(dev):
+            _lib.check(l.aid_encoder_forward(ctypes.byref(d), packed.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             batch, x.data_ptr(), int(is_u8), out.data_ptr(), _lib.stream_ptr(dev)),
+                       "aid_encoder_forward", l)
         return out

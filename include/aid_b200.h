@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AID_ABI_VERSION 1
+#define AID_ABI_VERSION 2
 
 /* LatentScoreNetwork dimensions — models/score_networks.py:20-29 */
 typedef struct AidScoreDims {
@@ -71,6 +71,10 @@ enum AidScoreBlockParam {
 };
 
 int32_t aid_abi_version(void);
+/* tensor-core operand element type this build of the library packs and multiplies: 0 = bf16
+ * (libaid_sm100.so), 1 = IEEE fp16 (libaid_sm100_f16.so: 11-bit significand, the TF32-class mode of
+ * the rel-1e-3 contract).  Packed buffers are only valid for the library that wrote them. */
+int32_t aid_operand_type(void);
 const char* aid_last_error(void);
 /* number of CUDA devices visible; <= 0 means the product path cannot run */
 int32_t aid_device_count(void);
@@ -86,8 +90,9 @@ int32_t aid_profile_select(int32_t epi, int32_t k, int32_t n);
 int32_t aid_profile_collect(double* total_ms_host, int64_t* launches_host);
 
 /* ---- weights ------------------------------------------------------------------------------
- * Derived cache of LatentScoreNetwork parameters: bf16 tcgen05 operand tiles (128x64, 128-byte
- * swizzle), the single-token attention folded to one HxH matrix, adaLN modulation rows
+ * Derived cache of LatentScoreNetwork parameters: 16-bit tcgen05 operand tiles (128 rows x 64
+ * columns, K-major NO-swizzle canonical layout: [16-byte K chunk][row][8 elements], one bulk copy
+ * per tile), the single-token attention folded to one HxH matrix, adaLN modulation rows
  * interleaved per 64 hidden columns, fp32 biases/LayerNorm affine/scalars.
  * Rebuild whenever the parameters change (optimizer.step / load_state_dict). */
 size_t aid_score_packed_bytes(const AidScoreDims* dims);
@@ -121,6 +126,31 @@ int32_t aid_sample(const AidScoreDims* dims, const void* packed, void* workspace
                    const float* coef_host, int32_t T, const float* observation,
                    const float* z_init, const float* noise, float* z_out, float* traj_out,
                    void* stream);
+
+/* Same loop with the noise source made explicit ("noise = injected pointer or Philox
+ * seed/offset").  z_init / noise as above when given.  With `philox` != NULL (DEVICE pointer to
+ * {uint64 seed, uint64 call offset}) every draw that was not injected is generated inside the
+ * kernels (csrc/philox.cuh: Philox4x32-10 + Box-Muller keyed by seed, call offset, draw index,
+ * GLOBAL row = row_offset + row, column): z_T by a fill kernel, the per-step eps in the epilogue
+ * of the last GEMM, so no [T-1,B,L] noise tensor exists.  The caller advances the device-side
+ * offset between calls (a replayed CUDA graph then draws fresh noise).  deterministic != 0: no
+ * per-step noise (core/diffusion.py:233).  The call enqueues only kernels, device-to-device
+ * copies and memsets on `stream` (no host-memory copies), so it can be captured in a CUDA graph. */
+typedef struct AidSampleNoise {
+  const float* z_init;        /* [B,L] or NULL (requires philox) */
+  const float* noise;         /* [n_draws,B,L] or NULL */
+  const void* philox;         /* device {uint64 seed, uint64 offset} or NULL */
+  int64_t row_offset;         /* global index of row 0 */
+  int32_t deterministic;
+} AidSampleNoise;
+int32_t aid_sample_ex(const AidScoreDims* dims, const void* packed, void* workspace,
+                      size_t workspace_bytes, int32_t batch, int32_t n_steps,
+                      const float* step_time_host, const int32_t* step_index_host,
+                      const float* coef_host, int32_t T, const float* observation,
+                      const AidSampleNoise* noise, float* z_out, float* traj_out, void* stream);
+/* out[rows, cols] (cols % 4 == 0) = the standard normals draw `draw` of the Philox stream above */
+int32_t aid_philox_normal(const void* philox, uint32_t draw, int64_t row_offset, float* out, int32_t rows,
+                          int32_t cols, void* stream);
 
 /* ---- EFE heads: policy / dynamics / value / reward -----------------------------------------
  * DiffusionConditionedPolicy (models/policy_networks.py:12-146, num_layers=3, state-dependent std),

@@ -17,14 +17,27 @@ def header_functions():
     return sorted(set(re.findall(r"\b(aid_[a-z0-9_]+)\s*\(", src)))
 
 
-def test_library_exports_every_declared_symbol():
+@pytest.mark.parametrize("operand,code", [("bf16", 0), ("f16", 1)])
+def test_library_exports_every_declared_symbol(operand, code):
+    """Both builds of the library (bf16 and fp16 tensor-core operands) load and export the header."""
     from active_inference_diffusion_b200 import _lib
-    lib = _lib.lib()
+    lib = _lib.lib(operand)
     names = header_functions()
     assert len(names) >= 18
     for n in names:
-        assert hasattr(lib, n), f"libaid_sm100.so does not export {n}"
-    assert lib.aid_abi_version() == 1
+        assert hasattr(lib, n), f"{_lib.LIB_PATHS[operand]} does not export {n}"
+    assert lib.aid_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.aid_operand_type() == code
+
+
+def test_operand_type_switch_is_scoped():
+    from active_inference_diffusion_b200 import _lib
+    assert _lib.operand_type() == "bf16"
+    with _lib.operand("f16"):
+        assert _lib.operand_type() == "f16" and _lib.lib().aid_operand_type() == 1
+    assert _lib.operand_type() == "bf16" and _lib.lib().aid_operand_type() == 0
+    with pytest.raises(ValueError):
+        _lib.set_operand_type("fp8")
 
 
 def test_size_queries_and_errors_without_gpu():
