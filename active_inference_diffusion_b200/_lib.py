@@ -187,6 +187,30 @@ def _declare_r2(l: ctypes.CDLL) -> None:
     l.aid_sample_ex.argtypes = [POINTER(AidScoreDims), c_void_p, c_void_p, c_size_t, c_int32, c_int32,
                                 POINTER(c_float), POINTER(c_int32), POINTER(c_float), c_int32, c_void_p,
                                 POINTER(AidSampleNoise), c_void_p, c_void_p, c_void_p]
+    D = POINTER(AidScoreDims)
+    l.aid_train_packed_bytes.restype = c_size_t
+    l.aid_train_packed_bytes.argtypes = [D]
+    l.aid_train_num_params.restype = c_int32
+    l.aid_train_num_params.argtypes = [D]
+    l.aid_train_pack.restype = c_int32
+    l.aid_train_pack.argtypes = [D, POINTER(c_void_p), c_int32, c_void_p, c_size_t, c_void_p]
+    l.aid_train_workspace_bytes.restype = c_size_t
+    l.aid_train_workspace_bytes.argtypes = [D, c_int32]
+    l.aid_train_debug_offset.restype = c_int64
+    l.aid_train_debug_offset.argtypes = [D, c_int32, c_char_p, c_int32]
+    l.aid_dsm_forward.restype = c_int32
+    l.aid_dsm_forward.argtypes = [D, c_void_p, c_void_p, c_size_t, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]
+    l.aid_gp_forward_backward.restype = c_int32
+    l.aid_gp_forward_backward.argtypes = [D, c_void_p, c_void_p, c_size_t, c_int32, c_int32, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, POINTER(c_void_p), c_void_p]
+    l.aid_dsm_backward.restype = c_int32
+    l.aid_dsm_backward.argtypes = [D, c_void_p, c_void_p, c_size_t, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
+                                   POINTER(c_void_p), c_void_p, c_void_p, c_void_p]
+    l.aid_wgrad_workspace_bytes.restype = c_size_t
+    l.aid_wgrad_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
+    l.aid_wgrad.restype = c_int32
+    l.aid_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p]
     l.aid_philox_normal.restype = c_int32
     l.aid_philox_normal.argtypes = [c_void_p, ctypes.c_uint32, c_int64, c_void_p, c_int32, c_int32, c_void_p]
 
@@ -375,6 +399,23 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = Non
     with torch.cuda.device(dev):
         check(l.aid_gemm_nt(ptr(a), a.stride(0), a.stride(1), ptr(b), b.stride(0), b.stride(1), ptr(bias), ptr(out),
                             M, N, K, prec, ptr(ws), ws_bytes, stream_ptr(dev)), "aid_gemm_nt", l)
+    return out
+
+
+def wgrad(dy: torch.Tensor, x: torch.Tensor, operand: Optional[str] = None) -> torch.Tensor:
+    """dy[rows,N]^T @ x[rows,K] -> [N,K] through the MN-major weight-gradient kernel (aid_wgrad)."""
+    dev = require_cuda(dy, x)
+    dy, x = f32c(dy), f32c(x)
+    rows, N = dy.shape
+    K = x.shape[1]
+    if x.shape[0] != rows:
+        raise ValueError("wgrad: row counts differ")
+    out = torch.empty(N, K, dtype=torch.float32, device=dev)
+    l = lib(operand)
+    nbytes = l.aid_wgrad_workspace_bytes(rows, N, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(l.aid_wgrad(ptr(dy), ptr(x), ptr(out), rows, N, K, ptr(ws), nbytes, stream_ptr(dev)), "aid_wgrad", l)
     return out
 
 

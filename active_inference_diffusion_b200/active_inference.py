@@ -16,6 +16,7 @@ Pixel observations (ConvDecoder, SpatialAttentionAggregator) are SURVEY §8(f) "
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Dict, Optional, Tuple, Union
 
@@ -28,7 +29,7 @@ from .diffusion import LatentDiffusionProcess
 from .heads import (DiffusionConditionedPolicy, HeadsBundle, LatentDynamicsModel, ValueNetwork,
                     make_reward_predictor)
 from .score_network import LatentScoreNetwork
-from . import _lib, autograd_path
+from . import _lib, autograd_path, train_native
 
 
 class FunctionSpaceEpistemicEstimator(nn.Module):
@@ -350,6 +351,16 @@ class DiffusionActiveInference(nn.Module):
     def _compute_latent_kl(self, latent: torch.Tensor, prior_latent: torch.Tensor) -> torch.Tensor:
         return 0.5 * torch.sum((latent - prior_latent) ** 2, dim=-1)
 
+    # Training path of compute_diffusion_elbo: "native" = hand-written forward / backward / double
+    # backward kernels for the trunk (csrc/train.inc) with `training_operand` tensor-core operands
+    # ("f16": TF32-class, the rel-1e-3 contract; "bf16": stated bf16 bound); "autograd" = the torch
+    # graph over aid_gemm_nt at autograd_path.PRECISION (any dims, any order of differentiation).
+    training_path = "native"
+    training_operand = "f16"
+
+    def _native_training(self) -> bool:
+        return self.training_path == "native" and train_native.supported(self.latent_score_network)
+
     ELBO_KEYS = ["reconstruction_loss", "kl_loss", "score_matching_loss", "elbo", "reward_loss", "grad_penalty",
                  "mean_time", "loss_weight_mean"]
 
@@ -378,7 +389,11 @@ class DiffusionActiveInference(nn.Module):
         B, dev = observations.shape[0], self.device
         if latents is None:
             latents = self.update_belief_via_diffusion(observations, raw_observations)["latent"]
-        recon = F.mse_loss(self.decode_observation(latents), observations)
+        # decoder / reward-head terms: their gradients are dropped by the reference's training step
+        # (agents/state_agent.py:225); `elbo_score_only` evaluates them without recording a graph
+        side = torch.no_grad() if getattr(self, "elbo_score_only", False) else contextlib.nullcontext()
+        with side:
+            recon = F.mse_loss(self.decode_observation(latents), observations)
         # t drawn here lies in [0,1): the score net's continuous-time branch (score_networks.py:121)
         # is known without reading the tensor back; an injected t is inspected as the reference does
         continuous = True if t is None else None
@@ -391,24 +406,38 @@ class DiffusionActiveInference(nn.Module):
         noisy, _, info_q = diff.continuous_q_sample(latents, t, noise)
         if continuous is None:
             continuous = bool(t.max() <= 1.0 and t.min() >= 0.0)
-        # the conditioning path (time embeddings, observation encoder, adaLN modulations) is the same
-        # for the score-matching forward and the gradient penalty's forward: evaluated once, shared
-        mod, time_weight = autograd_path.score_conditioning(self.latent_score_network, t, observations, B, continuous)
-        folds = autograd_path.fold_attention(self.latent_score_network)       # W_o W_v per block, shared too
-        pred = autograd_path.score_from_conditioning(self.latent_score_network, noisy, mod, time_weight, folds)
+        net = self.latent_score_network
+        if self._native_training():
+            # Native path (csrc/train.inc through train_native.trunk): ONE forward serves the
+            # score-matching term and the gradient penalty (both evaluate s_theta on the same numbers,
+            # :584 and :717); s and g = d(sum s)/dz come out of one autograd node whose backward runs
+            # the hand-written double backward.  The conditioning embedding and the attention fold stay
+            # in torch autograd (small GEMMs, fp32-class operands: their gradients carry no stream scale).
+            with autograd_path.precision("bf16" if self.training_operand == "bf16" else "bf16x3"):
+                cond, time_weight = autograd_path.score_cond_embedding(net, t, observations, B, continuous)
+                folds = autograd_path.fold_attention(net)
+            pred, g = train_native.trunk(net, noisy, cond, time_weight, folds, operand=self.training_operand)
+            gp = torch.mean((g.norm(2, dim=1) - 1.0) ** 2)
+        else:
+            # the conditioning path (time embeddings, observation encoder, adaLN modulations) is the
+            # same for the score-matching forward and the gradient penalty's forward: evaluated once
+            mod, time_weight = autograd_path.score_conditioning(net, t, observations, B, continuous)
+            folds = autograd_path.fold_attention(net)       # W_o W_v per block, shared too
+            pred = autograd_path.score_from_conditioning(net, noisy, mod, time_weight, folds)
+            gp = self._compute_gradient_penalty(noisy, t, observations, continuous, conditioning=(mod, time_weight, folds))
         sigma = info_q["sigma"]
         true_score = -noise / (sigma + 1e-8)
         w = diff.compute_loss_weight(t)
         per_sample = w.view(-1) * torch.sum((pred - true_score) ** 2, dim=1)
         sm = per_sample.mean()
-        gp = self._compute_gradient_penalty(noisy, t, observations, continuous, conditioning=(mod, time_weight, folds))
         if prior_eps is None:
             prior = diff.sample_latent_prior(B, dev)
         else:
             prior = diff.latent_prior_mean.unsqueeze(0) + torch.exp(diff.latent_prior_log_std).unsqueeze(0) * prior_eps
         kl = self._compute_latent_kl(latents, prior).mean()
         klw = torch.exp(-5.0 * t.mean())
-        pr = autograd_path.seq(self.reward_predictor, latents)
+        with side:
+            pr = autograd_path.seq(self.reward_predictor, latents)
         r_std = torch.exp(torch.clamp(pr[:, 1], min=-5, max=2))
         # -log N(r; m, s) written out (torch.distributions validates its arguments with a host sync)
         # (same expression as Normal.log_prob)

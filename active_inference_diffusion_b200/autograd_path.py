@@ -197,18 +197,14 @@ def _all_modulations(net, cond: torch.Tensor):
     return linear(F.silu(cond), w, b).split(2 * H, dim=-1)
 
 
-def score_conditioning(net, time: torch.Tensor, observation: Optional[torch.Tensor], batch: int,
-                       continuous: Optional[bool] = None):
-    """Everything of models/score_networks.py:101-171 that does not depend on z_t: time embeddings
-    (:117-141), observation encoder (:143-149), and the 13 adaLN modulations of their sum.  Returns
-    (modulations, time_weight or None).  The ELBO evaluates the score net twice on the same (t,
-    observation) -- the score-matching term and the gradient penalty (core/active_inference.py:584,717)
-    -- so it computes this once and shares it: one [B,512]x[512,13312] modulation GEMM (16 % of a
-    forward's FLOPs) and one backward of it instead of two; autograd sums both branches' gradients
-    into the shared tensor, so the parameter gradients are the same sums.
-    `continuous` states which time branch (:121) applies when the caller already knows it (the ELBO
-    draws t in [0,1) itself); None reads it from `time` as the reference does, which costs a host
-    sync and cannot be captured in a CUDA graph."""
+def score_cond_embedding(net, time: torch.Tensor, observation: Optional[torch.Tensor], batch: int,
+                         continuous: Optional[bool] = None):
+    """Time embeddings (models/score_networks.py:117-141) + observation encoder (:143-149): the
+    conditioning vector `cond` [B,H] every adaLN modulation reads, and the time weight of the
+    continuous branch (or None).  `continuous` states which time branch (:121) applies when the caller
+    already knows it (the ELBO draws t in [0,1) itself); None reads it from `time` as the reference
+    does, which costs a host sync and cannot be captured in a CUDA graph.  The observation encoder's
+    Dropout(0.1) follows `net.training` as in the reference."""
     H = net.hidden_dim
     if continuous is None:
         continuous = bool(time.max() <= 1.0 and time.min() >= 0.0)
@@ -223,12 +219,25 @@ def score_conditioning(net, time: torch.Tensor, observation: Optional[torch.Tens
         t_emb, time_weight = _time_embed(net, time), None
     if observation is not None:
         enc = net.obs_encoder
-        o = F.silu(enc[1](linear(observation, enc[0].weight, enc[0].bias)))
+        o = enc[3](F.silu(enc[1](linear(observation, enc[0].weight, enc[0].bias))))     # enc[3]: Dropout(0.1)
         o = F.silu(enc[5](linear(o, enc[4].weight, enc[4].bias)))
         o = enc[8](linear(o, enc[7].weight, enc[7].bias))
     else:
         o = torch.zeros(batch, H, device=time.device)
-    return _all_modulations(net, t_emb + o), time_weight
+    return t_emb + o, time_weight
+
+
+def score_conditioning(net, time: torch.Tensor, observation: Optional[torch.Tensor], batch: int,
+                       continuous: Optional[bool] = None):
+    """Everything of models/score_networks.py:101-171 that does not depend on z_t: the conditioning
+    embedding and the 13 adaLN modulations of it.  Returns (modulations, time_weight or None).  The
+    ELBO evaluates the score net twice on the same (t, observation) -- the score-matching term and the
+    gradient penalty (core/active_inference.py:584,717) -- so it computes this once and shares it: one
+    [B,512]x[512,13312] modulation GEMM (16 % of a forward's FLOPs) and one backward of it instead of
+    two; autograd sums both branches' gradients into the shared tensor, so the parameter gradients are
+    the same sums."""
+    cond, time_weight = score_cond_embedding(net, time, observation, batch, continuous)
+    return _all_modulations(net, cond), time_weight
 
 
 def fold_attention(net):

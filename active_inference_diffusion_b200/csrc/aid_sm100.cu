@@ -305,7 +305,11 @@ static int launch_gemm(const uint8_t* A, int row_tiles, const PLin& w, EpiArgs e
   // unit per pass so TMEM holds two units and the epilogue of unit u overlaps the MMAs of unit u+1
   // (a 512-column unit fills TMEM and serialises them: 248 us vs 103 us of MMA time for mlp.2 at
   // 65,536 rows).  The second pass over the same A row tile hits L2.
-  if constexpr (EPI == EPI_PACK || EPI == EPI_F32) {
+  if constexpr (EPI == EPI_DACT) {
+    if (ea.act == ACT_GELU) return launch_gemm_shape<EPI, ACT_GELU>(ga, ea, st, res, wide);
+    if (ea.act == ACT_SILU) return launch_gemm_shape<EPI, ACT_SILU>(ga, ea, st, res, wide);
+    return fail("launch_gemm<EPI_DACT>: activation must be GELU or SiLU");
+  } else if constexpr (EPI == EPI_PACK || EPI == EPI_F32) {
     switch (ea.act) {
       case ACT_SILU: return launch_gemm_shape<EPI, ACT_SILU>(ga, ea, st, res, wide);
       case ACT_RELU: return launch_gemm_shape<EPI, ACT_RELU>(ga, ea, st, res, wide);
@@ -1166,6 +1170,7 @@ extern "C" int32_t aid_gemm_nt(const float* a, int64_t a_rs, int64_t a_cs, const
 }
 
 #include "heads.inc"
+#include "train.inc"
 #include "belief.inc"
 #include "encoder.inc"
 

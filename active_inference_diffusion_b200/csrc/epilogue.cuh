@@ -13,6 +13,75 @@
 // 150-250 KB of SASS and stalled on instruction fetch (ncu: stall_no_instruction on top).
 // rt/nt: row tile / n-tile indices; r: row inside the tile.
 
+// ---- activation derivatives for the training epilogues (EPI_DACT) ------------------------------
+// GELU (exact, models/score_networks.py:199) through the Abramowitz-Stegun erf of act_gelu_as:
+// with e = exp(-x^2/2), q = poly(t) e:  Phi(x) = x < 0 ? q/2 : 1 - q/2,  phi(x) = e / sqrt(2 pi),
+// gelu = x Phi, gelu' = Phi + x phi, gelu'' = phi (2 - x^2).
+__device__ __forceinline__ void gelu_parts(float x, float& Phi, float& phi) {
+  const float y = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, y, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = __expf(-y * y);
+  const float hq = 0.5f * p * t * e;
+  Phi = x < 0.f ? hq : 1.0f - hq;
+  phi = e * 0.3989422804014327f;
+}
+template <int ACT>
+__device__ __forceinline__ float dact_f(float x) {
+  if constexpr (ACT == ACT_GELU) {
+    float Phi, phi;
+    gelu_parts(x, Phi, phi);
+    return x * Phi;
+  } else if constexpr (ACT == ACT_SILU) {
+    return x / (1.0f + __expf(-x));
+  } else {
+    return x;
+  }
+}
+template <int ACT>
+__device__ __forceinline__ float dact_d1(float x) {
+  if constexpr (ACT == ACT_GELU) {
+    float Phi, phi;
+    gelu_parts(x, Phi, phi);
+    return fmaf(x, phi, Phi);
+  } else if constexpr (ACT == ACT_SILU) {
+    const float s = 1.0f / (1.0f + __expf(-x));
+    return s * fmaf(x, 1.0f - s, 1.0f);
+  } else {
+    return 1.0f;
+  }
+}
+template <int ACT>
+__device__ __forceinline__ float dact_d2(float x) {
+  if constexpr (ACT == ACT_GELU) {
+    float Phi, phi;
+    gelu_parts(x, Phi, phi);
+    return phi * (2.0f - x * x);
+  } else if constexpr (ACT == ACT_SILU) {
+    const float s = 1.0f / (1.0f + __expf(-x));
+    return s * (1.0f - s) * fmaf(x, 1.0f - 2.0f * s, 2.0f);
+  } else {
+    return 0.0f;
+  }
+}
+// 8 packed 16-bit operand elements -> fp32
+__device__ __forceinline__ void unpack_op16x8(const uint4 v, float* out) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#ifdef AID_F16
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+#else
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+#endif
+    out[2 * i] = f.x;
+    out[2 * i + 1] = f.y;
+  }
+}
+
 template <int EPI>
 struct EpiState {
   float bias;        // bias[nt*128 + r] of the tile about to be processed
@@ -92,7 +161,7 @@ __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
 // only; measured SLOWER on B200 (mlp.0 epilogue compute 92 us vs 72 us: the FMA pipe, not the XU
 // pipe, becomes the bound), kept as an accuracy option.  -DAID_EXACT_GELU: libm erff.
 __device__ __forceinline__ void act_gelu2(float& a, float& b) {
-#if defined(AID_EXACT_GELU)
+#if defined(AID_EXACT_GELU) || defined(AID_F16)
   a = act_gelu(a); b = act_gelu(b);
 #elif !defined(AID_GELU_POLY)
   const float2 x = make_float2(a, b);
@@ -441,6 +510,86 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
       st.rstd = rsqrtf(m2 / (float)e.h_dim + 1e-5f);
       st.rt = rt2;
     }
+  } else if constexpr (EPI == EPI_DACT) {
+    // Training epilogues (train.inc).  One thread = one row; 32 columns per chunk.
+    const int srt = rt % e.src_rt;                       // row tile of the saved forward tensors
+    const bool first_half = rt < e.src_rt;
+    const float aux_scale = e.aux_scale ? __ldg(e.aux_scale) : 1.0f;
+    uint32_t raw[32];
+    tmem_ld32(tmem_tile, raw);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int n0 = nt * TILE_N + c * 32;
+      const int kb_out = n0 >> 6;
+      const bool in_range = kb_out < e.out_kb;           // uniform over the group
+      float pre[32];
+      uint4 ax[4];
+      if (e.dact_mode != DACT_FWD && in_range) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = e.pre_tiled[((size_t)srt * e.pre_ld4 + (n0 >> 2) + q) * TILE_M + r];
+          pre[q * 4 + 0] = v.x; pre[q * 4 + 1] = v.y; pre[q * 4 + 2] = v.z; pre[q * 4 + 3] = v.w;
+        }
+        if (e.dact_mode == DACT_HAT || (e.dact_mode == DACT_BWD && first_half && e.aux_in)) {
+          const __nv_bfloat16* at = e.aux_in + (size_t)(srt * e.out_kb + kb_out) * TILE_ELEMS;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            ax[q] = *reinterpret_cast<const uint4*>(at + (((n0 & 63) >> 3) + q) * (TILE_M * 8) + r * 8);
+        }
+      }
+      float y[32];
+      if (e.dact_mode == DACT_FWD) bias32_from_smem(sb, c * 32, y);
+      tmem_ld_wait();
+      if (e.dact_mode == DACT_FWD) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(raw[j]);
+      }
+      if (c + 1 < 4) tmem_ld32(tmem_tile + (c + 1) * 32, raw);
+      else acc_release(rel);
+      if (!in_range) continue;
+      __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
+      if (e.dact_mode == DACT_FWD) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          e.pre_tiled[((size_t)rt * e.pre_ld4 + (n0 >> 2) + q) * TILE_M + r] =
+              make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = dact_f<ACT>(y[j]);
+        store_packed32(tile, r, n0 & 63, y);
+      } else {
+        if (e.dact_mode == DACT_VJP && e.aux_out) {
+          __nv_bfloat16* at = e.aux_out + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
+          store_packed32(at, r, n0 & 63, y);
+        }
+        float g2[32];
+        if (e.dact_mode == DACT_HAT) {
+          float cv[32];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) unpack_op16x8(ax[q], cv + q * 8);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) g2[j] = (n0 + j < e.n_valid) ? y[j] * cv[j] * dact_d2<ACT>(pre[j]) * aux_scale : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = (n0 + j < e.n_valid) ? y[j] * dact_d1<ACT>(pre[j]) : 0.f;
+        if (e.dact_mode == DACT_BWD && first_half && e.aux_in) {
+          float av[32];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) unpack_op16x8(ax[q], av + q * 8);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] += av[j];
+        }
+        store_packed32(tile, r, n0 & 63, y);
+        if (e.dact_mode == DACT_HAT) {
+          __nv_bfloat16* at = e.aux_out + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
+          store_packed32(at, r, n0 & 63, g2);
+        }
+      }
+    }
   } else {  // EPI_SCORE
     uint32_t raw[32];
     const float mult = __ldg(e.out_mult);
@@ -469,6 +618,16 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
         }
       }
       tmem_ld_wait();
+      if (e.r_out && live) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int col = n0 + q * 4;
+          if (col + 3 < e.n_valid)
+            *reinterpret_cast<float4*>(e.r_out + (size_t)row * e.n_valid + col) =
+                make_float4(__uint_as_float(raw[q * 4 + 0]), __uint_as_float(raw[q * 4 + 1]),
+                            __uint_as_float(raw[q * 4 + 2]), __uint_as_float(raw[q * 4 + 3]));
+        }
+      }
       float y[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {

@@ -49,6 +49,15 @@ enum EpiKind : int {
   EPI_SCORE = 3,  // clamp/scale score, optional reverse-diffusion step -> z (fp32 row-major + packed)
   EPI_LNACT = 4,  // y = act(LayerNorm(acc + bias) * gamma + beta) (+ resid) -> packed bf16; the whole
                   // 512-column row is normalised from TMEM (CTA-pair kernel only, gemm2.cuh)
+  EPI_DACT = 5,   // training (train.inc): activation forward with the pre-activation saved, and the
+                  // products with act'(pre) / act''(pre) of the three backward passes
+};
+// EPI_DACT modes (ACT = GELU or SiLU; pre = saved pre-activation, tiled fp32)
+enum DactMode : int {
+  DACT_FWD = 1,   // y = acc + bias: pre <- y (saved), out_packed <- act(y)
+  DACT_VJP = 2,   // aux_out <- acc (cotangent before the activation), out_packed <- acc * act'(pre)
+  DACT_HAT = 3,   // out_packed <- acc * act'(pre); aux_out <- acc * aux_in * act''(pre) * aux_scale
+  DACT_BWD = 4,   // out_packed <- acc * act'(pre) (+ aux_in on the rows of the first src_rt row tiles)
 };
 
 // Implicit im2col of a 3x3 / stride-1 / padding-1 convolution (encoder.inc): the A operand is the
@@ -119,6 +128,15 @@ struct EpiArgs {
   long long row_offset;      // global index of row 0 (sharded batches draw the unsharded stream)
   float c_s1, c_ra, c_c1, c_c2, c_sigma;
   float* z_out;              // row-major fp32 (score or new z)
+  float* r_out;              // optional: the pre-clamp output (training keeps it for the clamp mask)
+  // EPI_DACT
+  int dact_mode;
+  float4* pre_tiled;         // [src_rt][pre_ld4][128]: written in DACT_FWD, read otherwise
+  int pre_ld4;
+  int src_rt;                // row tiles of the saved tensors; stacked cotangent rows use rt % src_rt
+  const __nv_bfloat16* aux_in;
+  __nv_bfloat16* aux_out;
+  const float* aux_scale;    // device scalar (DACT_HAT) or null
 };
 
 // The source address of K chunk g for row tile 0 depends only on g; it is tabulated in shared
@@ -175,9 +193,25 @@ __device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-
 // path evaluates x*Phi(x) with Phi(x) ~= 0.5(1+tanh(sqrt(2/pi)(x+0.044715x^3))) on the MUFU tanh
 // unit: |gelu_tanh - gelu_erf| <= 5e-4 absolute (worst near |x|~2.5), i.e. below the bf16 rounding
 // (2^-9 relative) applied to this output right after.  AID_EXACT_GELU restores erff.
+// fp16-operand builds (-DAID_F16, the rel-1e-3 mode) use erf in the Abramowitz-Stegun 7.1.26 form
+// (|erf error| <= 1.5e-7): with q = (a1 t + ... + a5 t^5) exp(-y^2), t = 1/(1 + p y), y = |x|/sqrt2,
+// 1 + erf(x/sqrt2) is q for x < 0 and 2 - q for x >= 0 -- no cancellation in the negative tail; one
+// MUFU reciprocal and one MUFU exponential per element.
+__device__ __forceinline__ float act_gelu_as(float x) {
+  const float y = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, y, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float q = p * t * __expf(-y * y);
+  return 0.5f * x * (x < 0.f ? q : 2.0f - q);
+}
 __device__ __forceinline__ float act_gelu(float x) {
 #ifdef AID_EXACT_GELU
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+#elif defined(AID_F16)
+  return act_gelu_as(x);
 #else
   const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
   float t;

@@ -235,6 +235,8 @@ class LatentDiffusionProcess(nn.Module):
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 body()                  # warm-up: one-time kernel attribute setup happens outside the capture
+                if state is not None:
+                    state[1] -= 1       # the warm-up pass is not a call of the noise stream
             torch.cuda.current_stream(dev).wait_stream(side)
             g["graph"] = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g["graph"]):

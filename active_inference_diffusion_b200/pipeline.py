@@ -102,10 +102,18 @@ class CandidateScorer(nn.Module):
             side.wait_stream(torch.cuda.current_stream(dev))
             prev = self.latent_diffusion.use_graph
             self.latent_diffusion.use_graph = False          # the sampler is captured as part of THIS graph
+            # the warm-up pass must not advance the noise streams: a captured call then draws what the
+            # directly launched call would have drawn from the same generator state
+            rng = torch.cuda.get_rng_state(dev)
+            philox = self.latent_diffusion.philox_state(dev).clone() \
+                if self.latent_diffusion.noise_source == "philox" else None
             try:
                 with torch.cuda.stream(side):
                     self._score(g["obs"], h, K, g["epi"])    # warm-up outside the capture
+                    if philox is not None:
+                        self.latent_diffusion.philox_state(dev).copy_(philox)
                 torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.set_rng_state(rng, dev)
                 g["graph"] = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g["graph"]):
                     g["out"] = self._score(g["obs"], h, K, g["epi"])

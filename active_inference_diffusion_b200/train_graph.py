@@ -43,6 +43,10 @@ class GraphedElboStep:
             list(ai.latent_score_network.parameters()) + list(ai.latent_diffusion.parameters()))
         self._owned = {id(p) for p in self.params}
         self._others = [p for p in ai.parameters() if id(p) not in self._owned]
+        # decoder / reward-head gradients are discarded below: when none of their parameters is owned,
+        # their loss terms are evaluated without recording a graph (no wasted backward GEMMs)
+        side = list(ai.observation_decoder.parameters()) + list(ai.reward_predictor.parameters())
+        self.score_only = not any(id(p) in self._owned for p in side)
         self.warmup = max(1, int(warmup))
         self.allreduce = allreduce
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -60,7 +64,12 @@ class GraphedElboStep:
             p.grad = None
         for p in self._others:
             p.grad = None
-        loss, vals = self.ai.elbo_device(self.obs, self.rewards, self.latents)
+        prev = getattr(self.ai, "elbo_score_only", False)
+        self.ai.elbo_score_only = self.score_only
+        try:
+            loss, vals = self.ai.elbo_device(self.obs, self.rewards, self.latents)
+        finally:
+            self.ai.elbo_score_only = prev
         loss.backward()
         self.ai._join_time_importance()   # the EMA ran beside the backward on its side stream
         for p in self._others:        # decoder / reward-head gradients are discarded (reference :225)

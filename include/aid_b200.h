@@ -152,6 +152,58 @@ int32_t aid_sample_ex(const AidScoreDims* dims, const void* packed, void* worksp
 int32_t aid_philox_normal(const void* philox, uint32_t draw, int64_t row_offset, float* out, int32_t rows,
                           int32_t cols, void* stream);
 
+/* ---- training: score matching + gradient penalty through the trunk of the score net -----------
+ * Reference: core/active_inference.py:584-606 (s_theta on the noised latent, score-matching
+ * term) and :709-729 (_compute_gradient_penalty: g = d(sum s)/dz with create_graph=True and the
+ * double backward of mean((|g|_2 - 1)^2)); network models/score_networks.py:151-171.
+ * The trunk = latent_proj, the DiT blocks (single-token attention folded to W_f = W_o W_v by the
+ * caller), norm_final and output_proj, clamp, output_multiplier and time weight.  Its conditioning
+ * input `cond` [B,H] (time embedding + observation embedding, pre-SiLU) and the fold stay with the
+ * caller's autograd; this library returns d cond and the gradients of the folded tensors.
+ * Four passes share one caller-owned workspace (csrc/train.inc; derivation oracle/manual_score_grad.py):
+ *   aid_dsm_forward                    s [B,L]
+ *   aid_gp_forward_backward(phase 0)   g [B,L] = d(sum s)/dz
+ *   aid_gp_forward_backward(phase 1)   adjoint of phase 0 for g_bar = dL/dg: WRITES the penalty's part
+ *                                      of the weight gradients into `grads`, leaves the second-order
+ *                                      terms in the workspace (s_bar is read for the common stream scale)
+ *   aid_dsm_backward                   backward for s_bar = dL/ds (+ the terms of phase 1 when
+ *                                      with_penalty != 0, accumulating into `grads`): every trunk
+ *                                      gradient, d cond [B,H], and dz [B,L] (score-matching stream
+ *                                      only: the reference detaches the penalty's input) unless NULL.
+ * params / grads: tables of DEVICE pointers, fp32 row-major, in this order:
+ *   latent_proj.weight [H,L], .bias [H], output_proj.0.weight [H/2,H], .bias [H/2],
+ *   output_proj.2.weight [L,H/2], output_multiplier [1],
+ *   W_mod [(2*blocks+1)*2H, H], b_mod [(2*blocks+1)*2H]   (adaLN_modulation.1 of norm1, norm2 of
+ *   every block in order, then norm_final, concatenated),
+ *   then per block: W_f [H,H], b_f [H], mlp.0.weight [4H,H], .bias [4H], mlp.2.weight [H,4H], .bias [H].
+ * tw: per-row time weight [B] of the continuous-time branch (models/score_networks.py:137,170) or NULL.
+ * AidScoreDims: latent_dim % 8 == 0, hidden_dim % 128 == 0 (obs_dim / time_embed_dim unused). */
+size_t aid_train_packed_bytes(const AidScoreDims* dims);
+int32_t aid_train_num_params(const AidScoreDims* dims);
+int32_t aid_train_pack(const AidScoreDims* dims, const float* const* params_host_table, int32_t num_params,
+                       void* packed, size_t packed_bytes, void* stream);
+size_t aid_train_workspace_bytes(const AidScoreDims* dims, int32_t batch);
+int32_t aid_dsm_forward(const AidScoreDims* dims, const void* packed, void* workspace, size_t workspace_bytes,
+                        int32_t batch, const float* z, const float* cond, const float* tw, float* score_out,
+                        void* stream);
+int32_t aid_gp_forward_backward(const AidScoreDims* dims, const void* packed, void* workspace,
+                                size_t workspace_bytes, int32_t batch, int32_t phase, const float* tw,
+                                float* g_out, const float* g_bar, const float* s_bar,
+                                float* const* grads_host_table, void* stream);
+int32_t aid_dsm_backward(const AidScoreDims* dims, const void* packed, void* workspace, size_t workspace_bytes,
+                         int32_t batch, const float* s_bar, const float* tw, const float* cond,
+                         int32_t with_penalty, float* const* grads_host_table, float* dz, float* dcond,
+                         void* stream);
+/* Primitive of the weight gradients: out[N,K] = dy[rows,N]^T x[rows,K], fp32 row-major in and out.
+ * Both operands are packed row-major (as the training passes' producers leave them) and read as
+ * MN-major tcgen05 operands: no transposed pack. */
+size_t aid_wgrad_workspace_bytes(int32_t rows, int32_t N, int32_t K);
+int32_t aid_wgrad(const float* dy, const float* x, float* out, int32_t rows, int32_t N, int32_t K,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* byte offset of a named saved tensor inside the workspace (tests compare them with the
+ * specification); -1 for an unknown name */
+int64_t aid_train_debug_offset(const AidScoreDims* dims, int32_t batch, const char* name, int32_t index);
+
 /* ---- EFE heads: policy / dynamics / value / reward -----------------------------------------
  * DiffusionConditionedPolicy (models/policy_networks.py:12-146, num_layers=3, state-dependent std),
  * LatentDynamicsModel (models/dynamics_models.py:9-67, num_layers=3), ValueNetwork

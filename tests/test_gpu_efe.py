@@ -189,6 +189,7 @@ def test_diffusion_elbo_loss_and_grads(precision, tol):
     from active_inference_diffusion_b200 import autograd_path as AP
     L, A, H, B = 32, 6, 128, 24
     ai, nets, cfg = make_ai(L, A, H)
+    ai.training_path = "autograd"      # the torch graph over aid_gemm_nt; the native path: test_gpu_train_native.py
     g = gen(21)
     obs = torch.randn(B, L, generator=g)
     rew = torch.randn(B, generator=g)

@@ -1,0 +1,250 @@
+"""Native training path (csrc/train.inc: aid_dsm_forward / aid_gp_forward_backward / aid_dsm_backward,
+aid_wgrad) on a B200, through the C ABI:
+
+* the MN-major weight-gradient GEMM vs torch, incl. ragged rows, odd feature-block counts, split-K;
+* every saved tensor of the four passes vs the hand-derived specification (oracle/manual_score_grad.py,
+  itself pinned to autograd on the oracle in tests/test_manual_score_grad.py);
+* `compute_diffusion_elbo` loss / info terms / all score-net and diffusion gradients (incl. the
+  gradient penalty's double backward) vs the oracle restatement of core/active_inference.py:533-636,
+  709-729 at toy dims AND at the BASELINE dims L=128, H=512, B=4096 (cfg#3 per-GPU batch), fp16
+  operands at rel 1e-3 (north_star fp32/TF32 bound) and bf16 operands at the stated 3e-2.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import manual_score_grad as M
+from oracle import restatement as R
+from tests.test_gpu_efe import make_ai
+from tests.util import gen, make_score_net, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f16": 1e-3, "bf16": 3e-2}
+
+
+@pytest.mark.parametrize("operand", ["f16", "bf16"])
+@pytest.mark.parametrize("rows,N,K", [(128, 128, 256), (300, 64, 64), (1000, 200, 520), (4096, 512, 2048),
+                                      (4096, 2048, 512), (777, 32, 128), (20000, 512, 128)])
+def test_wgrad_mn_major_kernel(rows, N, K, operand):
+    from active_inference_diffusion_b200 import _lib
+    g = gen(rows + N)
+    dy = torch.randn(rows, N, generator=g).cuda()
+    x = torch.randn(rows, K, generator=g).cuda()
+    got = _lib.wgrad(dy, x, operand)
+    dt = torch.float16 if operand == "f16" else torch.bfloat16
+    want = dy.to(dt).double().t() @ x.to(dt).double()           # operands rounded as the kernel rounds them
+    assert rel_l2(got, want) < 2e-6, rel_l2(got, want)
+    full = dy.double().t() @ x.double()
+    assert rel_l2(got, full) < (1e-3 if operand == "f16" else 8e-3)
+
+
+def _spec_inputs(net_params, t, obs, B, NB, dev, dtype):
+    p = {k: (v.to(dev, dtype) if v.is_floating_point() else v.to(dev)) for k, v in net_params.items()}
+    cond, tw = R.score_conditioning(p, t.to(dev, dtype), obs.to(dev, dtype), B)
+    names = [f"transformer_blocks.{i}.{n}" for i in range(NB) for n in ("norm1", "norm2")] + ["norm_final"]
+    mods = []
+    for n_ in names:
+        m = F.linear(F.silu(cond), p[n_ + ".adaLN_modulation.1.weight"], p[n_ + ".adaLN_modulation.1.bias"])
+        scale, shift = m.chunk(2, dim=-1)
+        mods.append((1 + scale, shift))
+    return p, cond, tw, mods
+
+
+@pytest.mark.parametrize("operand", ["f16", "bf16"])
+@pytest.mark.parametrize("continuous", [True, False])
+def test_native_trunk_saved_tensors_and_gradients_vs_specification(operand, continuous):
+    """Forward, VJP, adjoint-of-VJP and backward pass by pass against the specification in fp64."""
+    from active_inference_diffusion_b200 import autograd_path as AP, train_native as TN
+    L, O, H, NB, B = 32, 17, 128, 2, 200                      # two row tiles, the second ragged
+    tol = TOL[operand]
+    net, params = make_score_net(L, O, H, NB, device="cuda")
+    dev = torch.device("cuda", 0)
+    g = gen(5)
+    z = torch.randn(B, L, generator=g)
+    obs = torch.randn(B, O, generator=g)
+    t = torch.rand(B, generator=g) if continuous else torch.full((B,), 7.0)
+    tgt = torch.randn(B, L, generator=g)
+    wgt = torch.rand(B, generator=g)
+    # ---- specification (fp64 on the GPU)
+    p64, cond64, tw64, mods64 = _spec_inputs(params, t, obs, B, NB, dev, torch.float64)
+    T = M.Trunk.from_state_dict(p64)
+    s_w, g_w, sv = M.forward_and_vjp(T, z.to(dev, torch.float64), mods64, tw64)
+    s_l, g_l = s_w.clone().requires_grad_(True), g_w.clone().requires_grad_(True)
+    loss_w = (wgt.to(dev) * ((s_l - tgt.to(dev)) ** 2).sum(1)).mean() + 0.1 * ((g_l.norm(2, dim=1) - 1) ** 2).mean()
+    loss_w.backward()
+    G = M.backward(T, sv, s_l.grad, g_l.grad)
+    # ---- native
+    TN.KEEP_LAST = True
+    try:
+        zc = z.cuda().requires_grad_(True)
+        with AP.precision("bf16x3"):
+            cond, tw = AP.score_cond_embedding(net, t.cuda(), obs.cuda(), B, continuous)
+            folds = AP.fold_attention(net)
+        cond = cond.detach().requires_grad_(True)
+        s, gg = TN.trunk(net, zc, cond, tw, folds, operand=operand)
+        packed, ws = TN._Trunk.last
+    finally:
+        TN.KEEP_LAST = False
+    assert rel_l2(cond, cond64) < 1e-4
+    assert rel_l2(s, s_w) < tol, rel_l2(s, s_w)
+    assert rel_l2(gg, g_w) < tol, rel_l2(gg, g_w)
+    off = lambda name, i=0: TN.debug_offset(net, B, name, i, operand)
+    report = {}
+
+    def chk(name, got, want, scale=1.0, bound=None):
+        e = rel_l2(got * scale, want)
+        report[name] = e
+        assert e < (bound or 2 * tol), (name, e)
+
+    S_c = float(ws[off("scale"):off("scale") + 20].view(torch.float32)[3])
+    for i in range(NB):
+        k = sv["blk"][i]
+        chk(f"blk{i}.xn1", TN.unpack(ws, off("blk.xn1", i), B, H, operand), k["a1"])
+        chk(f"blk{i}.xn2", TN.unpack(ws, off("blk.xn2", i), B, H, operand), k["a2"])
+        chk(f"blk{i}.u", TN.untile(ws, off("blk.u", i), B, 4 * H), k["u"])
+        chk(f"blk{i}.v", TN.unpack(ws, off("blk.v", i), B, 4 * H, operand), k["v"])
+        chk(f"blk{i}.chB", TN.unpack(ws, off("blk.chB", i), B, H, operand), k["c_hB"], 1 / S_c)
+        chk(f"blk{i}.chA", TN.unpack(ws, off("blk.chA", i), B, H, operand), k["c_hA"], 1 / S_c)
+        chk(f"blk{i}.cv", TN.unpack(ws, off("blk.cv", i), B, 4 * H, operand), k["c_v"], 1 / S_c)
+        chk(f"blk{i}.cu", TN.unpack(ws, off("blk.cu", i), B, 4 * H, operand), k["c_u"], 1 / S_c)
+        chk(f"site{2 * i}.ca", TN.untile(ws, off("site.ca", 2 * i), B, H), k["c_a1"], 1 / S_c)
+        chk(f"site{2 * i + 1}.ca", TN.untile(ws, off("site.ca", 2 * i + 1), B, H), k["c_a2"], 1 / S_c)
+    chk("r", ws[off("r"):off("r") + B * L * 4].view(torch.float32).view(B, L), sv["r"])
+    chk("p", TN.untile(ws, off("p"), B, H // 2), sv["p"])
+    chk("q", TN.unpack(ws, off("q"), B, H // 2, operand), sv["q"])
+    chk("cr", TN.unpack(ws, off("cr"), B, L, operand), sv["c_r"], 1 / S_c)
+    chk("cq", TN.unpack(ws, off("cq"), B, H // 2, operand), sv["c_q"], 1 / S_c)
+    chk("cp", TN.unpack(ws, off("cp"), B, H // 2, operand), sv["c_p"], 1 / S_c)
+    chk("ch0", TN.unpack(ws, off("ch0"), B, H, operand), sv["c_h0"], 1 / S_c)
+    chk("site_f.ca", TN.untile(ws, off("site.ca", 2 * NB), B, H), sv["c_af"], 1 / S_c)
+    # ---- backward through the node
+    loss = (wgt.cuda() * ((s - tgt.cuda()) ** 2).sum(1)).mean() + 0.1 * ((gg.norm(2, dim=1) - 1) ** 2).mean()
+    assert abs(float(loss) - float(loss_w)) < tol * abs(float(loss_w))
+    for q in net.parameters():
+        q.grad = None
+    loss.backward()
+    S_b = float(ws[off("scale"):off("scale") + 20].view(torch.float32)[0])
+    for i in range(NB):
+        chk(f"site{2 * i}.gp", TN.untile(ws, off("site.gp", 2 * i), B, H), G["dbg"]["gp_h"][i]["h_in"], 1 / S_b, 4 * tol)
+        chk(f"site{2 * i + 1}.gp", TN.untile(ws, off("site.gp", 2 * i + 1), B, H), G["dbg"]["gp_h"][i]["h_mid"], 1 / S_b, 4 * tol)
+        chk(f"blk{i}.ugp", TN.unpack(ws, off("blk.ugp", i), B, 4 * H, operand), G["dbg"]["gp_h"][i]["u"], 1 / S_b, 4 * tol)
+    chk("site_f.gp", TN.untile(ws, off("site.gp", 2 * NB), B, H), G["dbg"]["gp_hf"], 1 / S_b, 4 * tol)
+    chk("pgp", TN.unpack(ws, off("pgp"), B, H // 2, operand), G["dbg"]["gp_p"], 1 / S_b, 4 * tol)
+    chk("dz", zc.grad, G["z"])
+    # modulation / conditioning gradient: chain the spec's d mods through the modulation Linears by autograd
+    cond_leaf = cond64.detach().requires_grad_(True)
+    outs, grads = [], []
+    names = [f"transformer_blocks.{i}.{n}" for i in range(NB) for n in ("norm1", "norm2")] + ["norm_final"]
+    pw = {n_: (p64[n_ + ".adaLN_modulation.1.weight"].detach().requires_grad_(True),
+               p64[n_ + ".adaLN_modulation.1.bias"].detach().requires_grad_(True)) for n_ in names}
+    for n_, (ds1, dsh) in zip(names, G["mods"]):
+        m = F.linear(F.silu(cond_leaf), *pw[n_])
+        outs.append(m); grads.append(torch.cat([ds1, dsh], dim=-1))
+    torch.autograd.backward(outs, grads)
+    chk("dcond", cond.grad, cond_leaf.grad, bound=4 * tol)
+    named = dict(net.named_parameters())
+    chk("d latent_proj.weight", named["latent_proj.weight"].grad, G["W_lp"])
+    chk("d latent_proj.bias", named["latent_proj.bias"].grad, G["b_lp"])
+    chk("d output_proj.0.weight", named["output_proj.0.weight"].grad, G["Wo0"])
+    chk("d output_proj.0.bias", named["output_proj.0.bias"].grad, G["bo0"])
+    chk("d output_proj.2.weight", named["output_proj.2.weight"].grad, G["Wo2"])
+    chk("d output_multiplier", named["output_multiplier"].grad, G["mult"])
+    for i in range(NB):
+        pre = f"transformer_blocks.{i}."
+        chk(f"d {pre}mlp.0.weight", named[pre + "mlp.0.weight"].grad, G["blocks"][i]["W1"])
+        chk(f"d {pre}mlp.0.bias", named[pre + "mlp.0.bias"].grad, G["blocks"][i]["b1"])
+        chk(f"d {pre}mlp.2.weight", named[pre + "mlp.2.weight"].grad, G["blocks"][i]["W2"])
+        chk(f"d {pre}mlp.2.bias", named[pre + "mlp.2.bias"].grad, G["blocks"][i]["b2"])
+    for n_ in names:
+        chk(f"d {n_}.weight", named[n_ + ".adaLN_modulation.1.weight"].grad, pw[n_][0].grad, bound=4 * tol)
+        chk(f"d {n_}.bias", named[n_ + ".adaLN_modulation.1.bias"].grad, pw[n_][1].grad, bound=4 * tol)
+    print({k: f"{v:.1e}" for k, v in report.items()})
+
+
+def _elbo_case(L, A, H, B, operand, tol, oracle_dtype):
+    from active_inference_diffusion_b200 import autograd_path as AP
+    ai, nets, cfg = make_ai(L, A, H)
+    ai.training_path, ai.training_operand = "native", operand
+    dev = torch.device("cuda", 0)
+    g = gen(21)
+    obs = torch.randn(B, L, generator=g)
+    rew = torch.randn(B, generator=g)
+    lat = torch.randn(B, L, generator=g)
+    t = torch.rand(B, generator=g)
+    n1 = torch.randn(B, L, generator=g)
+    n2 = torch.randn(B, L, generator=g)
+    loss, info = ai.compute_diffusion_elbo(obs.cuda(), rew.cuda(), lat.cuda(), t=t.cuda(), noise=n1.cuda(),
+                                           prior_eps=n2.cuda())
+    loss.backward()
+    # oracle on the GPU in `oracle_dtype` (TF32 off); it is device-agnostic plain torch
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        cast = lambda d: {k: (v.to(dev, oracle_dtype) if v.is_floating_point() else v.to(dev)) for k, v in d.items()}
+        sp = {k: v.requires_grad_(True) if v.is_floating_point() else v for k, v in cast(nets["score"]).items()}
+        dp = {k: cast(nets["diffusion"])[k].requires_grad_(True)
+              for k in ("latent_prior_mean", "latent_prior_log_std", "log_snr_min", "log_snr_max")}
+        ecfg = dict(kl_weight=cfg.kl_weight, diffusion_weight=cfg.diffusion_weight, reward_weight=cfg.reward_weight)
+        c = lambda x: x.to(dev, oracle_dtype)
+        want, winfo, per = R.diffusion_elbo(sp, dp, cast(nets["decoder"]), cast(nets["reward"]), ecfg, c(obs), c(rew),
+                                            c(lat), c(t), c(n1), c(n2))
+        want.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    assert abs(float(loss) - float(want)) < tol * abs(float(want)), (float(loss), float(want))
+    for k in ("score_matching_loss", "grad_penalty", "kl_loss", "reward_loss", "reconstruction_loss"):
+        assert abs(info[k] - float(winfo[k])) < tol * (abs(float(winfo[k])) + 1e-6), (k, info[k], float(winfo[k]))
+    worst, worst_k = 0.0, None
+    for k, p in ai.latent_score_network.named_parameters():
+        if p.grad is None:
+            assert sp[k].grad is None or float(sp[k].grad.abs().max()) == 0.0, k
+            continue
+        if float(sp[k].grad.abs().max()) == 0.0:
+            continue
+        e = rel_l2(p.grad, sp[k].grad)
+        if e > worst:
+            worst, worst_k = e, k
+    for k, p in ai.latent_diffusion.named_parameters():
+        if p.grad is not None and k in dp:
+            e = rel_l2(p.grad, dp[k].grad)
+            if e > worst:
+                worst, worst_k = e, "diffusion." + k
+    print(f"native elbo L{L} H{H} B{B} [{operand}]: loss {float(loss):.6f} vs {float(want):.6f}; worst gradient rel-L2 "
+          f"{worst:.2e} ({worst_k})")
+    assert worst < tol, (worst_k, worst)
+    return worst
+
+
+@pytest.mark.parametrize("operand", ["f16", "bf16"])
+def test_native_elbo_toy_dims(operand):
+    _elbo_case(32, 6, 128, 24, operand, TOL[operand], torch.float64)
+
+
+@pytest.mark.parametrize("operand", ["f16", "bf16"])
+def test_native_elbo_baseline_dims_b4096(operand):
+    """BASELINE cfg#3 dims (L=128, H=512, 6 blocks) at the 8-GPU per-rank batch of 4,096."""
+    _elbo_case(128, 6, 512, 4096, operand, TOL[operand], torch.float64)
+
+
+def test_native_elbo_without_penalty_or_input_gradient():
+    """The node also serves losses that use only s (no g), and inputs that need no dz."""
+    from active_inference_diffusion_b200 import autograd_path as AP, train_native as TN
+    L, O, H, NB, B = 32, 17, 128, 2, 130
+    net, params = make_score_net(L, O, H, NB, device="cuda")
+    g = gen(8)
+    z, obs, t = torch.randn(B, L, generator=g), torch.randn(B, O, generator=g), torch.rand(B, generator=g)
+    with AP.precision("bf16x3"):
+        cond, tw = AP.score_cond_embedding(net, t.cuda(), obs.cuda(), B, True)
+        folds = AP.fold_attention(net)
+    s, _ = TN.trunk(net, z.cuda(), cond, tw, folds, operand="f16")
+    (s ** 2).mean().backward()
+    p = {k: v.double().requires_grad_(True) if v.is_floating_point() else v for k, v in params.items()}
+    (R.score_forward(p, z.double(), t.double(), obs.double()) ** 2).mean().backward()
+    worst = 0.0
+    for k, q in net.named_parameters():
+        if q.grad is None or p[k].grad is None or float(p[k].grad.abs().max()) == 0.0:
+            continue
+        worst = max(worst, rel_l2(q.grad, p[k].grad))
+    print(f"score-only loss through the native node: worst gradient rel-L2 {worst:.2e}")
+    assert worst < 1e-3
