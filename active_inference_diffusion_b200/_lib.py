@@ -206,7 +206,7 @@ def _declare_r2(l: ctypes.CDLL) -> None:
                                           c_void_p, c_void_p, POINTER(c_void_p), c_void_p]
     l.aid_dsm_backward.restype = c_int32
     l.aid_dsm_backward.argtypes = [D, c_void_p, c_void_p, c_size_t, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
-                                   POINTER(c_void_p), c_void_p, c_void_p, c_void_p]
+                                   POINTER(c_void_p), c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     l.aid_wgrad_workspace_bytes.restype = c_size_t
     l.aid_wgrad_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
     l.aid_wgrad.restype = c_int32

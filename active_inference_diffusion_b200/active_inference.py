@@ -29,7 +29,7 @@ from .diffusion import LatentDiffusionProcess
 from .heads import (DiffusionConditionedPolicy, HeadsBundle, LatentDynamicsModel, ValueNetwork,
                     make_reward_predictor)
 from .score_network import LatentScoreNetwork
-from . import _lib, autograd_path, train_native
+from . import _lib, autograd_path, distributed, train_native
 
 
 class FunctionSpaceEpistemicEstimator(nn.Module):
@@ -435,7 +435,11 @@ class DiffusionActiveInference(nn.Module):
         else:
             prior = diff.latent_prior_mean.unsqueeze(0) + torch.exp(diff.latent_prior_log_std).unsqueeze(0) * prior_eps
         kl = self._compute_latent_kl(latents, prior).mean()
-        klw = torch.exp(-5.0 * t.mean())
+        # data parallel: the KL weight reads the mean t of the GLOBAL batch (one scalar all-reduce), so
+        # the sharded step is the single-process step on the concatenated batch
+        group = getattr(self, "data_parallel_group", None)
+        t_mean = distributed.allreduce_mean(t.mean(), group) if group is not None else t.mean()
+        klw = torch.exp(-5.0 * t_mean)
         with side:
             pr = autograd_path.seq(self.reward_predictor, latents)
         r_std = torch.exp(torch.clamp(pr[:, 1], min=-5, max=2))
@@ -447,6 +451,8 @@ class DiffusionActiveInference(nn.Module):
         elbo = -recon + c.kl_weight * kl * klw + c.diffusion_weight * sm + 0.1 * gp - c.reward_weight * rl
         self._update_time_importance(t, per_sample.detach())
         vals = torch.stack([recon, kl, sm, elbo, rl, gp, t.mean(), w.mean()]).detach()
+        if group is not None:
+            vals = distributed.allreduce_mean(vals, group)       # the metrics of the global batch
         return -elbo, vals
 
     def compute_lambda_returns(self, rewards: torch.Tensor, values: torch.Tensor, next_values: torch.Tensor,
@@ -505,6 +511,9 @@ class DiffusionActiveInference(nn.Module):
         if side is None or side.device != t.device:
             side = self._ti_stream = torch.cuda.Stream(device=t.device)
         t, loss = t.detach(), loss.detach()
+        group = getattr(self, "data_parallel_group", None)
+        if group is not None:
+            t, loss = distributed.gather_time_loss(t, loss, group)   # identical EMA on every rank
         side.wait_stream(main)
         with torch.cuda.stream(side):
             _lib.time_importance_update(t, loss, w)

@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(256) k_clamp_seed(const float* __restrict__ rr
                                                     __nv_bfloat16* __restrict__ dst, int row_tiles, int kb_alloc,
                                                     int mode, float* __restrict__ part) {
   __shared__ float red[256];
-  const float m = __ldg(mult) * mul * ((mul_dev && mode == 1) ? __ldg(mul_dev) : 1.0f);
+  const float m = __ldg(mult) * mul * ((mul_dev && mode != 2) ? __ldg(mul_dev) : 1.0f);
   const size_t total = (size_t)row_tiles * kb_alloc * 1024;
   float acc = 0.f;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;

@@ -56,30 +56,79 @@ def global_argmin(local_efe: torch.Tensor, row_offset: int) -> Tuple[int, float]
     return int(cand[:, 1].min().item()), float(best.item())
 
 
-def allreduce_grads(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20) -> None:
-    """Average gradients over ranks in flat buckets (one collective per ~64 MB: NVSwitch makes
-    cost latency-, not link-bound, so few large buckets)."""
-    if not dist.is_initialized() or dist.get_world_size() == 1:
-        return
-    world = dist.get_world_size()
-    grads = [p.grad for p in params if p.grad is not None]
-    bucket, size = [], 0
-    def flush():
-        nonlocal bucket, size
-        if not bucket:
+class FlatGrads:
+    """Persistent flat gradient buffer for a set of parameters: `.grad` of every parameter is a view
+    into one contiguous fp32 tensor, so the data-parallel exchange is ONE all-reduce on that tensor with
+    no staging copies (`torch.cat` / `copy_` back), and autograd accumulates straight into it."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views, off = [], 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def zero_and_attach(self) -> None:
+        """Zero the buffer and make it the parameters' `.grad` (call before backward)."""
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def allreduce(self, group=None) -> None:
+        if self.flat.numel() == 0 or not dist.is_initialized() or dist.get_world_size(group) == 1:
             return
-        flat = torch.cat([g.reshape(-1) for g in bucket])
-        dist.all_reduce(flat)
-        flat.div_(world)
+        dist.all_reduce(self.flat, group=group)
+        self.flat.mul_(1.0 / dist.get_world_size(group))
+
+
+def allreduce_mean(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Average of a small device tensor over ranks (mean t of the KL weight, the loss metrics)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return t
+    out = t.detach().clone()
+    dist.all_reduce(out, group=group)
+    return out / dist.get_world_size(group)
+
+
+def gather_time_loss(t: torch.Tensor, loss: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather of the per-sample (t_b, loss_b) pairs in rank order: every rank then applies the
+    identical sequential time-importance EMA (core/active_inference.py:750-771) over the GLOBAL batch,
+    exactly as one process would on the concatenated batch (equal shard sizes)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return t, loss
+    world = dist.get_world_size(group)
+    pair = torch.stack([t.detach().float().reshape(-1), loss.detach().float().reshape(-1)], dim=1).contiguous()
+    out = torch.empty(world * pair.shape[0], 2, dtype=pair.dtype, device=pair.device)
+    dist.all_gather_into_tensor(out, pair, group=group)
+    return out[:, 0].contiguous(), out[:, 1].contiguous()
+
+
+def allreduce_grads(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20, group=None) -> None:
+    """Average the gradients of `params` over ranks.  Gradients that already live in one contiguous
+    buffer (FlatGrads) go out as one collective; others are exchanged tensor by tensor, largest first
+    (NVSwitch: the cost is latency-, not link-bound, and no staging copy is made)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    world = dist.get_world_size(group)
+    grads = [p.grad for p in params if p.grad is not None]
+    small = [g for g in grads if g.numel() * g.element_size() < (1 << 20)]
+    large = [g for g in grads if g.numel() * g.element_size() >= (1 << 20)]
+    for g in large:
+        if g.is_contiguous():
+            dist.all_reduce(g, group=group)
+            g.mul_(1.0 / world)
+        else:
+            c = g.contiguous()
+            dist.all_reduce(c, group=group)
+            g.copy_(c.mul_(1.0 / world))
+    if small:
+        flat = torch.cat([g.reshape(-1) for g in small])          # < 1 MB each: one coalesced collective
+        dist.all_reduce(flat, group=group)
+        flat.mul_(1.0 / world)
         off = 0
-        for g in bucket:
-            n = g.numel()
-            g.copy_(flat[off:off + n].view_as(g))
-            off += n
-        bucket, size = [], 0
-    for g in grads:
-        bucket.append(g)
-        size += g.numel() * g.element_size()
-        if size >= bucket_bytes:
-            flush()
-    flush()
+        for g in small:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()

@@ -147,6 +147,9 @@ def make_reward_predictor(latent_dim: int, hidden_dim: int) -> nn.Sequential:
                          nn.Linear(hidden_dim, hidden_dim // 2), nn.ReLU(), nn.Linear(hidden_dim // 2, 2))
 
 
+F16_MAX_HORIZON = 10
+
+
 def _bundle_of(module: nn.Module) -> "HeadsBundle":
     owner = getattr(module, "_owner", None)
     if owner is None:
@@ -236,6 +239,12 @@ class HeadsBundle:
         tau = _lib.f32c(preference_temperature.detach().reshape(1))
         B, d = latent.shape[0], self.dims()
         K, h = num_trajectories, horizon
+        if _lib.operand_type() == "f16" and h > F16_MAX_HORIZON:
+            # predict_next_latent doubles the latent every step (mean = 2 z + f(z, a)):
+            # after ~14 steps |z| passes the largest fp16 number (65504) and the operand conversion would
+            # saturate.  bf16 operands (8-bit exponent) have no such limit.
+            raise RuntimeError(f"fp16 tensor-core operands cover rollouts of at most {F16_MAX_HORIZON} steps "
+                               f"(got horizon {h}): use the bf16 operand type for longer horizons")
         assert tuple(policy_noise.shape) == (K * h, B, d.action_dim), policy_noise.shape
         assert tuple(reparam_noise.shape) == (K * h, B, d.latent_dim), reparam_noise.shape
         efe = torch.empty(B, dtype=torch.float32, device=dev)

@@ -101,6 +101,32 @@ class LatentScoreNetwork(nn.Module):
         # derived caches (not part of the state_dict)
         object.__setattr__(self, "_cache", _lib.PackedCache())
 
+    @torch.no_grad()
+    def randomize_zero_init(self, seed: int = 123, output_multiplier: Optional[float] = None) -> None:
+        """Give the tensors the reference zero-initialises (adaLN modulations :254-255, the last output
+        weight :99, the DiT MLP biases :211-212) seeded random values.  At construction the score is
+        identically zero, so synthetic-weight throughput and parity runs call this to
+        exercise real operand values (tensor-pipe power is data dependent).  Every tensor gets its own
+        generator stream keyed by (seed, position in the sorted parameter names)."""
+        named = dict(self.named_parameters())
+        for i, k in enumerate(sorted(named)):
+            p = named[k]
+            g = torch.Generator().manual_seed(seed * 100003 + i)
+            if k.endswith("adaLN_modulation.1.weight"):
+                v = torch.randn(p.shape, generator=g) * (0.5 / p.shape[1] ** 0.5)
+            elif k.endswith("adaLN_modulation.1.bias"):
+                v = torch.randn(p.shape, generator=g) * 0.1
+            elif k.endswith("output_proj.2.weight"):
+                v = torch.randn(p.shape, generator=g) * (1.0 / p.shape[1] ** 0.5)
+            elif k.endswith("mlp.0.bias") or k.endswith("mlp.2.bias"):
+                v = torch.randn(p.shape, generator=g) * 0.02
+            elif k.endswith("output_multiplier") and output_multiplier is not None:
+                v = torch.full(p.shape, float(output_multiplier))
+            else:
+                continue
+            p.copy_(v.to(p.device, p.dtype))
+        self._cache.invalidate()
+
     # ---- derived cache -------------------------------------------------------------------
     @property
     def num_blocks(self) -> int:

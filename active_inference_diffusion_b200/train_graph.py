@@ -9,8 +9,9 @@ per-GPU batches of the data-parallel configuration (4,096-8,192 rows) the step i
 the graph removes every launch gap and all Python/autograd dispatch from it.  There is no host read
 inside the step: the loss and the eight metrics stay on the device until the caller asks.
 
-The gradient all-reduce (NCCL) runs after the replay on the same stream, outside the graph, so the
-captured step is identical at any world size.
+Under torchrun the gradient exchange is part of the step (and of the graph): the trunk's backward
+all-reduces each stage's gradients on a side stream while the next stage computes
+(train_native._Trunk.backward), and the remaining parameters go out as one flat collective.
 """
 from __future__ import annotations
 
@@ -18,7 +19,9 @@ from typing import Dict, Iterable, List, Optional, Tuple
 
 import torch
 
-from . import distributed
+import torch.distributed as dist
+
+from . import distributed, train_native
 
 
 class GraphedElboStep:
@@ -58,19 +61,40 @@ class GraphedElboStep:
         self.latents = torch.zeros(self.batch_size, L, device=dev)
         self.loss: Optional[torch.Tensor] = None
         self.metrics: Optional[torch.Tensor] = None
+        # data parallel (one process per GPU): the trunk's backward averages its own gradients stage by
+        # stage, overlapped with the following stages (train_native); the remaining parameters
+        # (conditioning path, diffusion parameters) accumulate into one flat buffer that is exchanged as
+        # a single collective after backward.  All of it is enqueued inside the step, i.e. inside the
+        # captured graph.
+        self.group = dist.group.WORLD if (allreduce and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.flat_rest: Optional[distributed.FlatGrads] = None
+        if self.group is not None:
+            native = ai._native_training()
+            done = {id(p) for p in train_native.reduced_parameters(ai.latent_score_network)} if native else set()
+            self._reduced = [p for p in self.params if id(p) in done]
+            self.flat_rest = distributed.FlatGrads([p for p in self.params if id(p) not in done])
+            ai.data_parallel_group = self.group
 
     def _eager(self) -> Tuple[torch.Tensor, torch.Tensor]:
         for p in self.params:
             p.grad = None
         for p in self._others:
             p.grad = None
+        if self.flat_rest is not None:
+            self.flat_rest.zero_and_attach()
+            train_native.DATA_PARALLEL_GROUP = self.group if self.ai._native_training() else None
         prev = getattr(self.ai, "elbo_score_only", False)
         self.ai.elbo_score_only = self.score_only
         try:
             loss, vals = self.ai.elbo_device(self.obs, self.rewards, self.latents)
         finally:
             self.ai.elbo_score_only = prev
-        loss.backward()
+        try:
+            loss.backward()
+        finally:
+            train_native.DATA_PARALLEL_GROUP = None
+        if self.flat_rest is not None:
+            self.flat_rest.allreduce(self.group)
         self.ai._join_time_importance()   # the EMA ran beside the backward on its side stream
         for p in self._others:        # decoder / reward-head gradients are discarded (reference :225)
             p.grad = None
@@ -100,8 +124,6 @@ class GraphedElboStep:
         if self.graph is None:
             self._capture()
         self.graph.replay()
-        if self.allreduce:
-            distributed.allreduce_grads(self.params)
         return self.loss, self.metrics
 
     def metrics_dict(self) -> Dict[str, float]:

@@ -21,6 +21,7 @@ import ctypes
 from typing import List, Optional, Sequence, Tuple
 
 import torch
+import torch.distributed as dist
 
 from . import _lib
 
@@ -108,24 +109,85 @@ class _Trunk(torch.autograd.Function):
         B = cond.shape[0]
         s_bar = torch.zeros(B, dims.latent_dim, device=dev) if s_bar is None else _lib.f32c(s_bar)
         with_penalty = g_bar is not None
-        grads = [torch.empty(shape, dtype=torch.float32, device=dev) for shape in ctx.shapes]
+        nb = dims.num_blocks
+        # One flat gradient buffer, laid out stage by stage of aid_dsm_backward (output head, blocks from
+        # the last to the first, latent_proj + modulation Linear): a stage's gradients are contiguous,
+        # so the data-parallel all-reduce of a finished stage is ONE collective on a slice, with no
+        # staging copies; the tensors handed to autograd are views of it.
+        order = [2, 3, 4, 5] + [HEAD_PARAMS + BLOCK_PARAMS * i + j for i in reversed(range(nb)) for j in range(BLOCK_PARAMS)] \
+            + [0, 1, 6, 7]
+        sizes = [int(torch.Size(ctx.shapes[i]).numel()) for i in order]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        grads, off, bounds = [None] * len(order), 0, {}
+        for i, n in zip(order, sizes):
+            grads[i] = flat[off:off + n].view(ctx.shapes[i])
+            bounds[i] = (off, off + n)
+            off += n
+        stage_slices = [(bounds[2][0], bounds[5][1])] + \
+            [(bounds[HEAD_PARAMS + BLOCK_PARAMS * i][0], bounds[HEAD_PARAMS + BLOCK_PARAMS * i + BLOCK_PARAMS - 1][1])
+             for i in reversed(range(nb))] + [(bounds[0][0], bounds[7][1])]
         table = _table(grads)
         need_dz = ctx.needs_input_grad[2]
         dz = torch.empty(B, dims.latent_dim, dtype=torch.float32, device=dev) if need_dz else None
         dcond = torch.empty_like(cond)
         st = _lib.stream_ptr(dev)
         wbytes = ctx.ws.numel()
+        group = DATA_PARALLEL_GROUP if (DATA_PARALLEL_GROUP is not None and dist.is_initialized()
+                                        and dist.get_world_size(DATA_PARALLEL_GROUP) > 1) else None
+
+        def run(lo, hi):
+            _lib.check(l.aid_dsm_backward(ctypes.byref(dims), ctx.packed.data_ptr(), ctx.ws.data_ptr(), wbytes, B,
+                                          s_bar.data_ptr(), _lib.ptr(tw), cond.data_ptr(), int(with_penalty), table,
+                                          _lib.ptr(dz), dcond.data_ptr(), lo, hi, st), "aid_dsm_backward", l)
+
         with torch.cuda.device(dev):
             if with_penalty:
                 g_bar = _lib.f32c(g_bar)
                 _lib.check(l.aid_gp_forward_backward(ctypes.byref(dims), ctx.packed.data_ptr(), ctx.ws.data_ptr(), wbytes,
                                                      B, 1, _lib.ptr(tw), None, g_bar.data_ptr(), s_bar.data_ptr(), table,
                                                      st), "aid_gp_forward_backward(phase 1)", l)
-            _lib.check(l.aid_dsm_backward(ctypes.byref(dims), ctx.packed.data_ptr(), ctx.ws.data_ptr(), wbytes, B,
-                                          s_bar.data_ptr(), _lib.ptr(tw), cond.data_ptr(), int(with_penalty), table,
-                                          _lib.ptr(dz), dcond.data_ptr(), st), "aid_dsm_backward", l)
+            if group is None:
+                run(0, nb + 2)
+            else:
+                # gradient all-reduce overlapped with the remaining stages: NCCL on a side stream that
+                # waits for the stage just enqueued; the main stream joins before the gradients are used
+                main = torch.cuda.current_stream(dev)
+                side = _side_stream(dev)
+                world = dist.get_world_size(group)
+                for stage, (a, b) in enumerate(stage_slices):
+                    run(stage, stage + 1)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        dist.all_reduce(flat[a:b], group=group)
+                main.wait_stream(side)
+                flat.mul_(1.0 / world)
         ctx.ws = ctx.packed = None           # the saved activations are dead: release them to the allocator
         return (None, None, dz, dcond, None) + tuple(grads)
+
+
+# Data-parallel training: when set (train_graph.GraphedElboStep does it under torchrun), the trunk's
+# backward all-reduces (averages) its own gradients stage by stage, overlapped with the computation of
+# the following stages.  The parameters covered are `reduced_parameters(net)`; the caller all-reduces
+# the rest (conditioning path, diffusion parameters) after backward.
+DATA_PARALLEL_GROUP = None
+_SIDE = {}
+
+
+def _side_stream(dev: torch.device) -> torch.cuda.Stream:
+    s = _SIDE.get(dev)
+    if s is None:
+        s = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def reduced_parameters(net) -> List[torch.nn.Parameter]:
+    """Parameters whose gradients come exclusively through the trunk node (and are therefore already
+    averaged over ranks when DATA_PARALLEL_GROUP is set): latent_proj, the DiT blocks (incl. the
+    attention tensors reached through the fold and the adaLN modulations), norm_final, output_proj,
+    output_multiplier."""
+    out = list(net.latent_proj.parameters()) + list(net.transformer_blocks.parameters()) + \
+        list(net.norm_final.parameters()) + list(net.output_proj.parameters()) + [net.output_multiplier]
+    return out
 
 
 def trunk(net, z: torch.Tensor, cond: torch.Tensor, time_weight: Optional[torch.Tensor], folds,

@@ -176,6 +176,9 @@ int32_t aid_philox_normal(const void* philox, uint32_t draw, int64_t row_offset,
  *   W_mod [(2*blocks+1)*2H, H], b_mod [(2*blocks+1)*2H]   (adaLN_modulation.1 of norm1, norm2 of
  *   every block in order, then norm_final, concatenated),
  *   then per block: W_f [H,H], b_f [H], mlp.0.weight [4H,H], .bias [4H], mlp.2.weight [H,4H], .bias [H].
+ * aid_dsm_backward runs stages [stage_begin, stage_end) of 2 + num_blocks (0: output head; 1+k: block
+ * num_blocks-1-k; last: latent_proj, dz, modulation Linear, d cond): a data-parallel caller all-reduces
+ * a finished stage's gradients on another stream while the next stage computes.  (0, 2+num_blocks) = all.
  * tw: per-row time weight [B] of the continuous-time branch (models/score_networks.py:137,170) or NULL.
  * AidScoreDims: latent_dim % 8 == 0, hidden_dim % 128 == 0 (obs_dim / time_embed_dim unused). */
 size_t aid_train_packed_bytes(const AidScoreDims* dims);
@@ -193,7 +196,7 @@ int32_t aid_gp_forward_backward(const AidScoreDims* dims, const void* packed, vo
 int32_t aid_dsm_backward(const AidScoreDims* dims, const void* packed, void* workspace, size_t workspace_bytes,
                          int32_t batch, const float* s_bar, const float* tw, const float* cond,
                          int32_t with_penalty, float* const* grads_host_table, float* dz, float* dcond,
-                         void* stream);
+                         int32_t stage_begin, int32_t stage_end, void* stream);
 /* Primitive of the weight gradients: out[N,K] = dy[rows,N]^T x[rows,K], fp32 row-major in and out.
  * Both operands are packed row-major (as the training passes' producers leave them) and read as
  * MN-major tcgen05 operands: no transposed pack. */

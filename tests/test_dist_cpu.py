@@ -60,3 +60,65 @@ def test_two_rank_sharding_argmin_and_grad_allreduce():
         assert gathered_ok
         assert idx == int(torch.argmin(efe)) == 17 and val == -9.0
         assert torch.allclose(grad, w.grad, rtol=1e-5, atol=1e-6)
+
+
+def _worker_plumbing(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from active_inference_diffusion_b200.distributed import FlatGrads, allreduce_mean, gather_time_loss
+    from oracle import restatement as R
+    g = torch.Generator().manual_seed(3)
+    B = 64
+    t_all, loss_all = torch.rand(world * B, generator=g), torch.rand(world * B, generator=g) * 3
+    t, loss = t_all[rank * B:(rank + 1) * B], loss_all[rank * B:(rank + 1) * B]
+    # (t, loss) all-gather in rank order -> the sequential time-importance EMA of the GLOBAL batch
+    tg, lg = gather_time_loss(t, loss)
+    w = R.update_time_importance(torch.ones(100), tg, lg)
+    # scalar all-reduce: mean t of the global batch (KL weight) from the local means
+    t_mean = allreduce_mean(t.mean())
+    # flat gradient buffer: autograd accumulates into the views, one collective, no staging copies
+    lin = torch.nn.Linear(5, 3)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        for p in lin.parameters():
+            p.copy_(torch.randn(p.shape, generator=torch.Generator().manual_seed(1)))
+    fg = FlatGrads(lin.parameters())
+    fg.zero_and_attach()
+    x = torch.randn(world * 16, 5, generator=torch.Generator().manual_seed(2))[rank * 16:(rank + 1) * 16]
+    (lin(x) ** 2).mean().backward()
+    assert lin.weight.grad.data_ptr() == fg.views[0].data_ptr()      # accumulated in place, still a view
+    fg.allreduce()
+    q.put((rank, torch.equal(tg, t_all) and torch.equal(lg, loss_all), w, float(t_mean), fg.flat.clone()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_training_plumbing_time_importance_gather_scalar_mean_flat_grads():
+    """the (t_b, loss_b) all-gather gives every rank the identical time-importance EMA,
+    the mean-t scalar all-reduce equals the global mean, and the flat-buffer gradient exchange equals the
+    single-process gradient of the concatenated batch."""
+    from oracle import restatement as R
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_plumbing, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(3)
+    t_all, loss_all = torch.rand(world * 64, generator=g), torch.rand(world * 64, generator=g) * 3
+    w_want = R.update_time_importance(torch.ones(100), t_all, loss_all)
+    lin = torch.nn.Linear(5, 3)
+    with torch.no_grad():
+        for p in lin.parameters():
+            p.copy_(torch.randn(p.shape, generator=torch.Generator().manual_seed(1)))
+    x = torch.randn(world * 16, 5, generator=torch.Generator().manual_seed(2))
+    (lin(x) ** 2).mean().backward()
+    want = torch.cat([lin.weight.grad.reshape(-1), lin.bias.grad.reshape(-1)])
+    for rank, gathered_ok, w, t_mean, flat in out:
+        assert gathered_ok
+        assert torch.equal(w, w_want)                      # bit-identical EMA on every rank
+        assert abs(t_mean - float(t_all.mean())) < 1e-6
+        assert torch.allclose(flat, want, rtol=1e-5, atol=1e-6)
