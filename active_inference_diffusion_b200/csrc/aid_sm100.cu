@@ -31,8 +31,25 @@ static int fail(const std::string& msg) {
     if (_e != cudaSuccess)                                                                \
       return fail(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
   } while (0)
+// AID_SEGV_BT=1: print a native backtrace on SIGSEGV (developer aid; resolve with addr2line on the .so)
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void aid_segv_handler(int) {
+  void* bt[64];
+  const int n = backtrace(bt, 64);
+  backtrace_symbols_fd(bt, n, 2);
+  _exit(139);
+}
+static const bool g_segv_bt = [] {
+  if (getenv("AID_SEGV_BT") && atoi(getenv("AID_SEGV_BT")) != 0) signal(SIGSEGV, aid_segv_handler);
+  return true;
+}();
+// AID_TRACE=1: print every launch site to stderr (developer aid for locating host-side faults)
+static const bool g_trace = getenv("AID_TRACE") && atoi(getenv("AID_TRACE")) != 0;
 #define AID_LAUNCH_CHECK(name)                                                            \
   do {                                                                                    \
+    if (g_trace) { fprintf(stderr, "[aid] %s\n", name); fflush(stderr); }                 \
     ++g_launches;                                                                         \
     cudaError_t _e = cudaGetLastError();                                                  \
     if (_e != cudaSuccess) return fail(std::string(name) + ": " + cudaGetErrorString(_e)); \

@@ -643,8 +643,7 @@ __global__ void __launch_bounds__(1024) k_amax_scale(const float* __restrict__ a
 }
 
 // out[i] = in[i] * mul * (*mul_dev)
-__global__ void k_scale_copy(const float* __restrict__ in, size_t n, float mul, const float* __restrict__ mul_dev,
-                             float* __restrict__ out) {
+__global__ void k_scale_copy(const float* in, size_t n, float mul, const float* __restrict__ mul_dev, float* out) {
   const float m = mul * (mul_dev ? __ldg(mul_dev) : 1.0f);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = in[i] * m;
