@@ -117,12 +117,13 @@ class _Trunk(torch.autograd.Function):
         order = [2, 3, 4, 5] + [HEAD_PARAMS + BLOCK_PARAMS * i + j for i in reversed(range(nb)) for j in range(BLOCK_PARAMS)] \
             + [0, 1, 6, 7]
         sizes = [int(torch.Size(ctx.shapes[i]).numel()) for i in order]
-        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        padded = [(n + 3) // 4 * 4 for n in sizes]            # every tensor starts 16-byte aligned (128-bit stores)
+        flat = torch.zeros(sum(padded), dtype=torch.float32, device=dev)
         grads, off, bounds = [None] * len(order), 0, {}
-        for i, n in zip(order, sizes):
+        for i, n, m in zip(order, sizes, padded):
             grads[i] = flat[off:off + n].view(ctx.shapes[i])
-            bounds[i] = (off, off + n)
-            off += n
+            bounds[i] = (off, off + m)
+            off += m
         stage_slices = [(bounds[2][0], bounds[5][1])] + \
             [(bounds[HEAD_PARAMS + BLOCK_PARAMS * i][0], bounds[HEAD_PARAMS + BLOCK_PARAMS * i + BLOCK_PARAMS - 1][1])
              for i in reversed(range(nb))] + [(bounds[0][0], bounds[7][1])]

@@ -26,6 +26,9 @@ pytestmark = pytest.mark.gpu
 # next to it (the precision class the bound is named after).
 TOL = {"f16": 1e-3, "bf16": 3e-2}
 GRAD_TOL = {"f16": 2e-3, "bf16": 3e-2}
+# one-element parameters (output_multiplier, time_scale, freq_scale): their gradient is ONE number, a
+# cancelling sum over the whole batch, so its relative error is a single noisy draw rather than a norm
+SCALAR_GRAD_TOL = {"f16": 6e-3, "bf16": 8e-2}
 
 
 @pytest.mark.parametrize("operand", ["f16", "bf16"])
@@ -157,7 +160,7 @@ def test_native_trunk_saved_tensors_and_gradients_vs_specification(operand, cont
     chk("d output_proj.0.weight", named["output_proj.0.weight"].grad, G["Wo0"])
     chk("d output_proj.0.bias", named["output_proj.0.bias"].grad, G["bo0"])
     chk("d output_proj.2.weight", named["output_proj.2.weight"].grad, G["Wo2"])
-    chk("d output_multiplier", named["output_multiplier"].grad, G["mult"])
+    chk("d output_multiplier", named["output_multiplier"].grad, G["mult"], bound=SCALAR_GRAD_TOL[operand])
     for i in range(NB):
         pre = f"transformer_blocks.{i}."
         chk(f"d {pre}mlp.0.weight", named[pre + "mlp.0.weight"].grad, G["blocks"][i]["W1"])
@@ -204,7 +207,7 @@ def _elbo_case(L, A, H, B, operand, tol, oracle_dtype):
     assert abs(float(loss) - float(want)) < tol * abs(float(want)), (float(loss), float(want))
     for k in ("score_matching_loss", "grad_penalty", "kl_loss", "reward_loss", "reconstruction_loss"):
         assert abs(info[k] - float(winfo[k])) < tol * (abs(float(winfo[k])) + 1e-6), (k, info[k], float(winfo[k]))
-    worst, worst_k = 0.0, None
+    worst, worst_k, worst_s, worst_sk = 0.0, None, 0.0, None
     for k, p in ai.latent_score_network.named_parameters():
         if p.grad is None:
             assert sp[k].grad is None or float(sp[k].grad.abs().max()) == 0.0, k
@@ -212,15 +215,21 @@ def _elbo_case(L, A, H, B, operand, tol, oracle_dtype):
         if float(sp[k].grad.abs().max()) == 0.0:
             continue
         e = rel_l2(p.grad, sp[k].grad)
-        if e > worst:
+        if p.numel() == 1:
+            if e > worst_s:
+                worst_s, worst_sk = e, k
+        elif e > worst:
             worst, worst_k = e, k
     for k, p in ai.latent_diffusion.named_parameters():
         if p.grad is not None and k in dp:
             e = rel_l2(p.grad, dp[k].grad)
-            if e > worst:
+            if p.numel() == 1:
+                if e > worst_s:
+                    worst_s, worst_sk = e, "diffusion." + k
+            elif e > worst:
                 worst, worst_k = e, "diffusion." + k
     print(f"native elbo L{L} H{H} B{B} [{operand}]: loss {float(loss):.6f} vs {float(want):.6f}; worst gradient rel-L2 "
-          f"{worst:.2e} ({worst_k})")
+          f"{worst:.2e} ({worst_k}); worst one-element parameter {worst_s:.2e} ({worst_sk})")
     if operand == "f16":
         # the same oracle graph on torch's TF32 matmuls (cuBLAS): the precision class of the contract
         torch.backends.cuda.matmul.allow_tf32 = True
@@ -234,10 +243,13 @@ def _elbo_case(L, A, H, B, operand, tol, oracle_dtype):
             w32.backward()
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev[0]
-        tf32_worst = max(rel_l2(sp32[k].grad, sp[k].grad) for k in sp32
-                         if sp32[k].is_floating_point() and sp32[k].grad is not None and float(sp[k].grad.abs().max()) > 0)
-        print(f"    torch TF32 matmuls on the oracle graph: worst gradient rel-L2 {tf32_worst:.2e}")
+        live = [k for k in sp32 if sp32[k].is_floating_point() and sp32[k].grad is not None and float(sp[k].grad.abs().max()) > 0]
+        tf32_worst = max(rel_l2(sp32[k].grad, sp[k].grad) for k in live if sp32[k].numel() > 1)
+        tf32_scalar = max(rel_l2(sp32[k].grad, sp[k].grad) for k in live if sp32[k].numel() == 1)
+        print(f"    torch TF32 matmuls on the oracle graph: worst gradient rel-L2 {tf32_worst:.2e}; one-element "
+              f"parameters {tf32_scalar:.2e}")
     assert worst < GRAD_TOL[operand], (worst_k, worst)
+    assert worst_s < SCALAR_GRAD_TOL[operand], (worst_sk, worst_s)
     return worst
 
 
