@@ -183,6 +183,10 @@ def _declare_colsum(l: ctypes.CDLL) -> None:
 def _declare_r2(l: ctypes.CDLL) -> None:
     """Round-2 entry points (include/aid_b200.h)."""
     l.aid_operand_type.restype = c_int32
+    l.aid_profile_select_slot.restype = c_int32
+    l.aid_profile_select_slot.argtypes = [c_int32, c_int32, c_int32, c_int32]
+    l.aid_profile_collect_slot.restype = c_int32
+    l.aid_profile_collect_slot.argtypes = [c_int32, POINTER(ctypes.c_double), POINTER(c_int64)]
     l.aid_sample_ex.restype = c_int32
     l.aid_sample_ex.argtypes = [POINTER(AidScoreDims), c_void_p, c_void_p, c_size_t, c_int32, c_int32,
                                 POINTER(c_float), POINTER(c_int32), POINTER(c_float), c_int32, c_void_p,
@@ -479,12 +483,17 @@ def lambda_returns(rewards: torch.Tensor, next_values: torch.Tensor, dones: torc
     return out.reshape(rewards.shape)
 
 
-def profile_select(epi: int, k: int = 0, n: int = 0) -> None:
-    check(lib().aid_profile_select(epi, k, n), "aid_profile_select")
+def profile_select(epi: int, k: int = 0, n: int = 0, slot: Optional[int] = None) -> None:
+    """Time every tcgen05 GEMM launch of the class (epilogue kind, K, N) with CUDA events on the launching
+    stream; `slot` (0..3) keeps several classes at once, None = slot 0 only (others cleared)."""
+    if slot is None:
+        check(lib().aid_profile_select(epi, k, n), "aid_profile_select")
+    else:
+        check(lib().aid_profile_select_slot(slot, epi, k, n), "aid_profile_select_slot")
 
 
-def profile_collect():
+def profile_collect(slot: int = 0):
     """(total device ms, launches) of the selected GEMM class since the last collect."""
     ms, n = ctypes.c_double(0.0), c_int64(0)
-    check(lib().aid_profile_collect(ctypes.byref(ms), ctypes.byref(n)), "aid_profile_collect")
+    check(lib().aid_profile_collect_slot(slot, ctypes.byref(ms), ctypes.byref(n)), "aid_profile_collect_slot")
     return ms.value, int(n.value)

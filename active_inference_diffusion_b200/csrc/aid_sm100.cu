@@ -158,36 +158,62 @@ struct GemmProfile {
   std::vector<cudaEvent_t> ev;   // start/stop pairs
   size_t used = 0;
 };
-static GemmProfile g_prof;
+constexpr int PROF_SLOTS = 4;
+static GemmProfile g_prof[PROF_SLOTS];
 
-extern "C" int32_t aid_profile_select(int32_t epi, int32_t k, int32_t n) {
-  g_prof.on = epi >= 0;
-  g_prof.epi = epi;
-  g_prof.kb = (k + TILE_K - 1) / TILE_K;
-  g_prof.n_tiles = (n + TILE_N - 1) / TILE_N;
-  g_prof.used = 0;
+static int prof_set(int slot, int32_t epi, int32_t k, int32_t n) {
+  GemmProfile& p = g_prof[slot];
+  p.on = epi >= 0;
+  p.epi = epi;
+  p.kb = (k + TILE_K - 1) / TILE_K;
+  p.n_tiles = (n + TILE_N - 1) / TILE_N;
+  p.used = 0;
   return 0;
 }
-extern "C" int32_t aid_profile_collect(double* total_ms, int64_t* launches) {
+// slot 0 only (and clears the other slots): the round-1 interface
+extern "C" int32_t aid_profile_select(int32_t epi, int32_t k, int32_t n) {
+  for (int i = 1; i < PROF_SLOTS; ++i) prof_set(i, -1, 0, 0);
+  return prof_set(0, epi, k, n);
+}
+extern "C" int32_t aid_profile_select_slot(int32_t slot, int32_t epi, int32_t k, int32_t n) {
+  if (slot < 0 || slot >= PROF_SLOTS) return fail("aid_profile_select_slot: slot out of range");
+  return prof_set(slot, epi, k, n);
+}
+static int prof_collect(int slot, double* total_ms, int64_t* launches) {
+  GemmProfile& p = g_prof[slot];
   double tot = 0;
-  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
-    AID_CHECK(cudaEventSynchronize(g_prof.ev[i + 1]));
+  for (size_t i = 0; i + 1 < p.used; i += 2) {
+    AID_CHECK(cudaEventSynchronize(p.ev[i + 1]));
     float ms = 0;
-    AID_CHECK(cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]));
+    AID_CHECK(cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]));
     tot += ms;
   }
   if (total_ms) *total_ms = tot;
-  if (launches) *launches = (int64_t)(g_prof.used / 2);
-  g_prof.used = 0;
+  if (launches) *launches = (int64_t)(p.used / 2);
+  p.used = 0;
   return 0;
 }
-static cudaEvent_t prof_event() {
-  if (g_prof.used == g_prof.ev.size()) {
+extern "C" int32_t aid_profile_collect(double* total_ms, int64_t* launches) { return prof_collect(0, total_ms, launches); }
+extern "C" int32_t aid_profile_collect_slot(int32_t slot, double* total_ms, int64_t* launches) {
+  if (slot < 0 || slot >= PROF_SLOTS) return fail("aid_profile_collect_slot: slot out of range");
+  return prof_collect(slot, total_ms, launches);
+}
+// slot whose selection matches this launch, or -1
+static int prof_match(int epi, int kb, int n_tiles) {
+  for (int i = 0; i < PROF_SLOTS; ++i) {
+    const GemmProfile& p = g_prof[i];
+    if (p.on && p.epi == epi && p.kb == kb && p.n_tiles == n_tiles && p.used < 200000) return i;
+  }
+  return -1;
+}
+static cudaEvent_t prof_event(int slot) {
+  GemmProfile& p = g_prof[slot];
+  if (p.used == p.ev.size()) {
     cudaEvent_t e;
     cudaEventCreate(&e);
-    g_prof.ev.push_back(e);
+    p.ev.push_back(e);
   }
-  return g_prof.ev[g_prof.used++];
+  return p.ev[p.used++];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -211,9 +237,9 @@ static int launch_gemm_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t 
   const int units = (ga.splits > 1 ? ga.splits : 1) * ga.row_tiles * (ga.n_tiles / (NW * G));
   int grid = units < num_sms() ? units : num_sms();
   if (grid < 1) return 0;
-  const bool prof = g_prof.on && g_prof.epi == EPI && g_prof.kb == ga.kb && g_prof.n_tiles == ga.n_tiles &&
-                    g_prof.used < 200000;
-  if (prof) cudaEventRecord(prof_event(), st);
+  const int pslot = prof_match(EPI, ga.kb, ga.n_tiles);
+  const bool prof = pslot >= 0;
+  if (prof) cudaEventRecord(prof_event(pslot), st);
   {
     // programmatic stream serialization: this grid may begin (prologue only, see pdl_wait in the
     // kernel) while the previous kernel of the stream drains
@@ -230,7 +256,7 @@ static int launch_gemm_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t 
     cfg.numAttrs = (pdl && !prof) ? 1 : 0;
     AID_CHECK(cudaLaunchKernelEx(&cfg, kern, ga, ea, ring));
   }
-  if (prof) cudaEventRecord(prof_event(), st);
+  if (prof) cudaEventRecord(prof_event(pslot), st);
   AID_LAUNCH_CHECK("gemm_kernel");
   return 0;
 }
@@ -256,9 +282,9 @@ static int launch_gemm2_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t
   const int max_pairs = num_sms() / 2;
   const int pairs = units < max_pairs ? units : max_pairs;
   if (pairs < 1) return 0;
-  const bool prof = g_prof.on && g_prof.epi == EPI && g_prof.kb == ga.kb && g_prof.n_tiles == ga.n_tiles &&
-                    g_prof.used < 200000;
-  if (prof) cudaEventRecord(prof_event(), st);
+  const int pslot = prof_match(EPI, ga.kb, ga.n_tiles);
+  const bool prof = pslot >= 0;
+  if (prof) cudaEventRecord(prof_event(pslot), st);
   {
     static const bool pdl = !(getenv("AID_DEBUG") && (atoi(getenv("AID_DEBUG")) & 2048));
     cudaLaunchConfig_t cfg = {};
@@ -273,7 +299,7 @@ static int launch_gemm2_inst(const GemmArgs& ga, const EpiArgs& ea, cudaStream_t
     cfg.numAttrs = (pdl && !prof) ? 1 : 0;
     AID_CHECK(cudaLaunchKernelEx(&cfg, kern, ga, ea, ring));
   }
-  if (prof) cudaEventRecord(prof_event(), st);
+  if (prof) cudaEventRecord(prof_event(pslot), st);
   AID_LAUNCH_CHECK("gemm2_kernel");
   return 0;
 }

@@ -12,6 +12,12 @@ hidden 512, 6 DiT blocks, 65,536 candidates per GPU (weak scaling: every rank sc
   python bench.py --impl reference [...]                         # the reference algorithm on host cores
 Under torchrun (N>1) one process per GPU; rows are independent so there is no data-path collective,
 only the timing barrier / max-over-ranks.
+
+The same JSON line carries, as the "train" object, BASELINE.json configs[2]: the score-matching + VFE
+training step (compute_diffusion_elbo forward, backward and the gradient penalty's double backward on
+the native kernels of csrc/train.inc, as one CUDA graph) at GLOBAL batch 32,768 sharded over the ranks
+(strong scaling) with the NCCL gradient all-reduce overlapped with the backward pass -- the one path of
+the port with a collective.  `--no-train` / `--no-secondary` skip the extra legs.
 """
 from __future__ import annotations
 
@@ -92,6 +98,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def build_scorer(dev):
+    """Reference constructors under torch.manual_seed(0), then the zero-initialised tensors are
+    re-randomised (seed 123): SURVEY 8(d).  At construction the score is identically zero (all adaLN
+    modulations and the last output weight are zero), and tensor-pipe power depends on
+    the operand values, so throughput is measured on non-degenerate weights."""
+    import torch
+    from active_inference_diffusion_b200 import ActiveInferenceConfig, CandidateScorer, DiffusionConfig
+    torch.manual_seed(0)
+    cfg = ActiveInferenceConfig(latent_dim=L, hidden_dim=H, efe_horizon=HORIZON, device="cpu",
+                                diffusion=DiffusionConfig(num_diffusion_steps=T, beta_schedule="cosine"))
+    m = CandidateScorer(O, A, cfg).eval()
+    m.latent_score_network.randomize_zero_init(123)
+    return m.to(dev) if dev is not None else m
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the roofline kernels from the latest `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py from the committed CSV)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 def build_inputs(seed: int):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -118,13 +149,8 @@ def cpu_port_step(params, heads, sched, obs, seed):
 
 
 def cpu_models():
-    import torch
     from oracle import restatement as R
-    from active_inference_diffusion_b200 import ActiveInferenceConfig, CandidateScorer, DiffusionConfig
-    torch.manual_seed(0)
-    cfg = ActiveInferenceConfig(latent_dim=L, hidden_dim=H, efe_horizon=HORIZON, device="cpu",
-                                diffusion=DiffusionConfig(num_diffusion_steps=T, beta_schedule="cosine"))
-    m = CandidateScorer(O, A, cfg).eval()
+    m = build_scorer(None)
     sd = lambda mod: {k: v.detach().clone() for k, v in mod.state_dict().items()}
     heads = dict(policy=sd(m.policy_network), dynamics=sd(m.latent_dynamics), value=sd(m.value_network),
                  reward=sd(m.reward_predictor))
@@ -142,7 +168,49 @@ def time_cpu(steps: int, warmup: int):
     for i in range(steps):
         cpu_port_step(params, heads, sched, obs, 200 + i)
     dt = (time.perf_counter() - t0) / steps
-    return CPU_SAMPLE / dt, dt, torch.get_num_threads()
+    return CPU_SAMPLE / dt, dt, {"threads": torch.get_num_threads(), "host_cores": os.cpu_count()}
+
+
+def time_real_reference_sampler():
+    """When the unmodified reference package is importable on this box (oracle/ref_import.py: it exists
+    in the build container, not on the GPU box), time ITS reverse-diffusion loop
+    (core/diffusion.py:176-206 over models/score_networks.py) on the same sample next to the port's, so
+    the port's speed can be compared with the real modules.  The reference's EFE cannot run with the
+    epistemic term off (and crashes in state mode as shipped), so the arm's headline stays
+    the port of the whole workload."""
+    import torch
+    try:
+        from oracle import ref_import
+        if not ref_import.reference_available():
+            return {"available": False, "why": f"no reference package at {ref_import.REFERENCE_ROOT}"}
+        ref_import.import_reference()
+        from active_inference_diffusion.configs.config import DiffusionConfig as RefDiffusionConfig
+        from active_inference_diffusion.core.diffusion import LatentDiffusionProcess as RefDiffusion
+        from active_inference_diffusion.models.score_networks import LatentScoreNetwork as RefScoreNet
+        from oracle import restatement as R
+        torch.manual_seed(0)
+        net = RefScoreNet(L, O, H, num_layers=NB).eval()
+        ours = build_scorer(None).latent_score_network
+        net.load_state_dict(ours.state_dict())
+        dp = RefDiffusion(RefDiffusionConfig(num_diffusion_steps=T, beta_schedule="cosine"), latent_dim=L)
+        obs = build_inputs(1)[:CPU_SAMPLE]
+        params = {k: v.detach().clone() for k, v in ours.state_dict().items()}
+        sched = R.make_schedule(T, "cosine")
+        g = torch.Generator().manual_seed(5)
+        zT = torch.randn(CPU_SAMPLE, L, generator=g)
+        noise = [torch.randn(CPU_SAMPLE, L, generator=g) for _ in range(T - 1)]
+        with torch.no_grad():
+            dp.generate_latent_trajectory(net, CPU_SAMPLE, obs)
+            t0 = time.perf_counter()
+            dp.generate_latent_trajectory(net, CPU_SAMPLE, obs)
+            t_ref = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            R.generate_latent_trajectory(params, sched, zT, obs, noise)
+            t_port = time.perf_counter() - t0
+        return {"available": True, "sampler_s_reference_modules": t_ref, "sampler_s_port": t_port,
+                "candidates": CPU_SAMPLE, "note": "unmodified reference LatentScoreNetwork + LatentDiffusionProcess vs the oracle port"}
+    except Exception as e:
+        return {"available": False, "why": repr(e)}
 
 
 def run_reference_same_box(args):
@@ -197,8 +265,9 @@ def run_reference(args):
     if args.ref_device == "cuda":
         return run_reference_same_box(args)
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    value, dt, cores = time_cpu(steps, warmup)
-    cb = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+    value, dt, cpu = time_cpu(steps, warmup)
+    real = time_real_reference_sampler()
+    cb = {"value": value, "unit": UNIT, "cores": cpu["threads"], "host_cores": cpu["host_cores"], "kind": "port",
           "sample": f"{CPU_SAMPLE} candidates per step (BASELINE configs[0]); same T={T}, horizon={HORIZON}, K={K_TRAJ}; "
                     f"{steps} timed steps after {warmup} warm-up; torch fp32 oracle port of the reference algorithm "
                     "(/root/reference is not present on the GPU box)"}
@@ -210,14 +279,76 @@ def run_reference(args):
                                f"{CPU_SAMPLE}-candidate samples on host cores", "latent_dim": L, "hidden_dim": H,
                    "num_blocks": NB, "diffusion_steps": T, "horizon": HORIZON, "num_trajectories": K_TRAJ},
         "cpu_baseline": cb,
+        "reference_modules": real,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 # ---------------------------------------------------------------------------------------------
+TRAIN_GLOBAL_BATCH = 32768
+
+
+def bench_train(args, dev, world, rank, barrier):
+    """BASELINE configs[2]: one optimiser-ready training step of the score model (zero grads -> ELBO forward
+    -> backward incl. the gradient penalty's double backward -> time-importance EMA -> averaged
+    gradients in .grad) as ONE CUDA graph replay, global batch 32,768 sharded over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from active_inference_diffusion_b200 import ActiveInferenceConfig, DiffusionActiveInference, DiffusionConfig
+    from active_inference_diffusion_b200.train_graph import GraphedElboStep
+    torch.manual_seed(0)
+    cfg = ActiveInferenceConfig(latent_dim=L, hidden_dim=H, device="cpu", diffusion=DiffusionConfig(num_diffusion_steps=T))
+    ai = DiffusionActiveInference(L, A, L, cfg)
+    ai.latent_score_network.randomize_zero_init(123)
+    ai = ai.to(dev)
+    ai.use_epistemic = False
+    B = TRAIN_GLOBAL_BATCH // world
+    g = torch.Generator().manual_seed(7 + rank)
+    obs = torch.randn(B, L, generator=g).to(dev)
+    rew = torch.randn(B, generator=g).to(dev)
+    lat = torch.randn(B, L, generator=g).to(dev)
+    out = {}
+    for operand in ("f16", "bf16"):
+        ai.training_path, ai.training_operand = "native", operand
+        step = GraphedElboStep(ai, B)
+        for _ in range(2):
+            step(obs, rew, lat)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.train_steps):
+            step(obs, rew, lat)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / args.train_steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        loss = float(step.loss)
+        out[operand] = {"ms_per_step": float(ms), "samples_per_s": TRAIN_GLOBAL_BATCH / float(ms) * 1e3, "loss": loss}
+        del step
+    n_param = sum(p.numel() for p in ai.latent_score_network.parameters()) + sum(p.numel() for p in ai.latent_diffusion.parameters())
+    return {
+        "workload": "BASELINE configs[2]: score-matching + VFE training step fwd/bwd (+ gradient-penalty double backward), "
+                    f"global batch {TRAIN_GLOBAL_BATCH} over {world} rank(s), L={L} H={H} {NB} blocks, one CUDA graph per step",
+        "scaling": "strong", "global_batch": TRAIN_GLOBAL_BATCH, "per_rank_batch": B,
+        "metric": "training_samples_per_sec", "value": out["f16"]["samples_per_s"], "ms_per_step": out["f16"]["ms_per_step"],
+        "dtype": "f16 tensor-core operands (TF32-class 11-bit significand), fp32 accumulate",
+        "bf16_operands": out["bf16"],
+        "allreduce": None if world == 1 else {
+            "bytes_per_step": 4 * n_param, "overlapped": True,
+            "how": "NCCL all-reduce of each backward stage's gradients on a side stream while the next stage computes "
+                   "(train_native._Trunk.backward), remaining parameters as one flat collective; all inside the graph"},
+        "algorithmic_tflops": 7 * F_STEP * TRAIN_GLOBAL_BATCH / (out["f16"]["ms_per_step"] * 1e-3) / 1e12,
+        "flops_note": "7 trunk-forward equivalents per sample (forward, VJP, adjoint of the VJP with its weight "
+                      "gradients, backward with two input-gradient streams and one merged weight-gradient GEMM per layer); "
+                      "autograd on the reference formulation spends 9",
+        "loss_f16": out["f16"]["loss"], "loss_bf16": out["bf16"]["loss"],
+    }
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from active_inference_diffusion_b200 import ActiveInferenceConfig, CandidateScorer, DiffusionConfig, _lib
+    from active_inference_diffusion_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -229,10 +360,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    torch.manual_seed(0)
-    cfg = ActiveInferenceConfig(latent_dim=L, hidden_dim=H, efe_horizon=HORIZON, device="cpu",
-                                diffusion=DiffusionConfig(num_diffusion_steps=T, beta_schedule="cosine"))
-    model = CandidateScorer(O, A, cfg).eval().to(dev)
+    model = build_scorer(dev)
+    model.latent_diffusion.row_offset = rank * CANDIDATES      # Philox noise stream of the global row index
     obs_host = build_inputs(1 + rank).pin_memory()
     obs_dev = obs_host.to(dev)
 
@@ -271,8 +400,13 @@ def run_ours(args):
         step_resident()
     barrier()
 
-    # --- timed region (device-resident inputs); dominant-kernel events + clocks sampled inside it
-    _lib.profile_select(0, H, 4 * H)          # mlp.0: K=H, N=4H, bias + GELU -> packed bf16 epilogue
+    # --- timed region (device-resident inputs); roofline-kernel events + clocks sampled inside it
+    # slot 0: mlp.0  (EPI_PACK, K=H, N=4H: largest share of the step's FLOPs)
+    # slot 1: adaLN  (EPI_MODLN, K=H, N=2H: largest share of the step's TIME, 13 launches per denoise step)
+    # slot 2: mlp.2  (EPI_F32,  K=4H, N=H)
+    _lib.profile_select(0, H, 4 * H, slot=0)
+    _lib.profile_select(2, H, 2 * H, slot=1)
+    _lib.profile_select(1, 4 * H, H, slot=2)
     _lib.reset_launch_count()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -280,8 +414,9 @@ def run_ours(args):
     ms_step = timed(step_resident, args.steps)
     launches = _lib.launch_count()
     clk = clocks.stop() if rank == 0 else None
-    k_ms, k_n = _lib.profile_collect()
-    _lib.profile_select(-1)
+    prof = [_lib.profile_collect(i) for i in range(3)]
+    for i in range(3):
+        _lib.profile_select(-1, slot=i)
 
     # --- end to end: pinned host observations in, efe + first action back to the host, every step
     for _ in range(2):
@@ -292,20 +427,76 @@ def run_ours(args):
     value = total / (ms_step * 1e-3)
     e2e_value = total / (ms_e2e * 1e-3)
 
+    # --- secondary measurements (rank 0 of a single-GPU run only; short)
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        secondary = {}
+        with _lib.operand("f16"):
+            for _ in range(2):
+                step_resident()
+            ms16 = timed(step_resident, max(2, args.steps // 2))
+        secondary["f16_operands"] = {"ms_per_step": ms16, "value": CANDIDATES / ms16 * 1e3, "unit": UNIT,
+                                     "note": "same workload on IEEE fp16 tensor-core operands (11-bit significand = TF32 class; "
+                                             "parity rel 1e-3, tests/test_gpu_round2.py) with erf-accurate GELU"}
+        k10 = lambda: model(obs_dev, horizon=HORIZON, num_trajectories=10)
+        k10(); ms = timed(k10, 2)
+        secondary["num_trajectories_10"] = {"ms_per_step": ms, "value": CANDIDATES / ms * 1e3, "unit": UNIT,
+                                            "note": "K=10 rollouts per candidate (the reference default)"}
+        small = {}
+        for b in (1, 256, 4096):
+            o = obs_dev[:b].contiguous()
+            f = lambda: model(o, horizon=HORIZON, num_trajectories=K_TRAJ)
+            for _ in range(3):
+                f()
+            ms = timed(f, 5)
+            small[str(b)] = {"ms_per_call": ms, "value": b / ms * 1e3}
+        secondary["small_batches_cuda_graph"] = small
+        try:
+            secondary["gpu_eager_reference"] = eager_reference_on_gpu(dev, 16384)
+        except Exception as e:  # the oracle is test infrastructure: its absence must not fail the bench
+            secondary["gpu_eager_reference"] = {"unavailable": repr(e)}
+
+    train = None
+    if not args.no_train:
+        train = bench_train(args, dev, world, rank, barrier)
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, cores = time_cpu(3, 1)
-        cb = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+        v, dt, cpu = time_cpu(3, 1)
+        cb = {"value": v, "unit": UNIT, "cores": cpu["threads"], "host_cores": cpu["host_cores"], "kind": "port",
               "sample": f"{CPU_SAMPLE} candidates per step (BASELINE configs[0]), 3 timed steps after 1 warm-up, "
-                        "torch fp32 oracle port of the reference algorithm on the box's host cores"}
+                        "torch fp32 oracle port of the reference algorithm on the box's host cores, run in this process "
+                        "after the GPU legs (the stand-alone --impl reference arm measures ~15 % higher)"}
 
     if rank == 0:
         peaks = measured_peaks()
-        per_launch_ms = k_ms / max(k_n, 1)
-        fc1_flops = 2.0 * CANDIDATES * H * (4 * H)
-        achieved = fc1_flops / (per_launch_ms * 1e-3) / 1e12 if k_n else None
         peak = peaks["sustained"] or peaks["burst"]
+        traffic = ncu_traffic()
+
+        def kernel(slot, name, flops):
+            ms, n = prof[slot]
+            per = ms / max(n, 1)
+            ach = flops / (per * 1e-3) / 1e12 if n else None
+            return {"kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
+                    "launches_timed": n, "avg_launch_ms": per, "flops_per_launch": flops,
+                    "share_of_step_time": (ms / args.steps) / ms_step if n else None}
+
+        k_mlp0 = kernel(0, "gemm2_kernel<EPI_PACK,resident A,GELU> mlp.0 [65536x512]x[512x2048] + bias + GELU -> packed operand",
+                        2.0 * CANDIDATES * H * (4 * H))
+        k_adaln = kernel(1, "gemm2_kernel<EPI_MODLN,resident A> adaLN modulation [65536x512]x[512x1024] + LayerNorm-modulate -> "
+                            "packed operand (13 launches per denoise step: the largest share of the step's time)",
+                         2.0 * CANDIDATES * H * (2 * H))
+        k_mlp2 = kernel(2, "gemm2_kernel<EPI_F32,streamed A> mlp.2 [65536x2048]x[2048x512] + bias + residual + LayerNorm partials",
+                        2.0 * CANDIDATES * (4 * H) * H)
         step_tflops = F_CANDIDATE * CANDIDATES / (ms_step * 1e-3) / 1e12
+        roof = dict(k_mlp0)
+        roof.update({
+            "bound": "tensor",
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); burst figure {peaks['burst']}",
+            "traffic": traffic.get("mlp0_dram_bytes_per_launch"),
+            "traffic_note": traffic.get("note", "no ncu capture summary found (profiles/ncu_traffic.json)"),
+            "other_kernels": [k_adaln, k_mlp2],
+            "whole_step_tflops": step_tflops, "whole_step_frac_of_peak": step_tflops / peak})
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -315,25 +506,63 @@ def run_ours(args):
                             "cosine-schedule denoise steps (BASELINE configs[1])",
                 "candidates_per_gpu": CANDIDATES, "latent_dim": L, "hidden_dim": H, "num_blocks": NB,
                 "diffusion_steps": T, "horizon": HORIZON, "num_trajectories": K_TRAJ, "epistemic": "off",
+                "weights": "reference constructors, torch.manual_seed(0), zero-initialised tensors re-randomised (seed 123)",
+                "noise": "z_T and the 49 step noises drawn inside the kernels (Philox4x32-10 keyed by the global row index); "
+                         "policy / reparameterisation draws by torch on the device",
                 "parallelism": f"rows sharded over {world} rank(s), no data-path collective",
-                "l2": "working set per step (>1.5 GB of noise + >0.5 GB of activations) exceeds the 126 MB L2; no flush needed",
+                "l2": "working set per step (> 0.5 GB of activations per layer pass) exceeds the 126 MB L2; no flush needed",
                 "precision": "bf16 tensor-core operands, fp32 accumulate / LayerNorm / residual / reverse step"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": CANDIDATES * O * 4 * world, "d2h_bytes_per_step": CANDIDATES * (1 + A) * 4 * world},
             "gpu_launches": int(launches),
-            "roofline": {
-                "bound": "tensor", "kernel": "gemm2_kernel<EPI_PACK,resident A,GELU> (CTA-pair tcgen05 kernel; mlp.0: [65536x512]x[512x2048] + bias + GELU -> packed bf16; largest share of the step's FLOPs)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); burst figure {peaks['burst']}",
-                "launches_timed": k_n, "avg_launch_ms": per_launch_ms, "flops_per_launch": fc1_flops,
-                "traffic": 295.8e6, "traffic_note": "dram bytes read+written per launch (86.0 + 209.7 MB) from profiles/r1_ncu_full_gemm_kernels_v5_pairs.csv (ncu --set full); algorithmic: 67 MB packed A in + 268 MB packed activations out",
-                "whole_step_tflops": step_tflops, "whole_step_frac_of_peak": step_tflops / peak},
+            "roofline": roof,
             "cpu_baseline": cb,
+            "train": train,
+            "secondary": secondary,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def eager_reference_on_gpu(dev, B):
+    """The reference's algorithm as eager PyTorch fp32 (TF32 off, its defaults) on THIS GPU: the
+    'same box' bar of SURVEY 8(d).  Uses the oracle port (test infrastructure) as the checker-side
+    implementation; one timed pass over B candidates."""
+    import torch
+    from oracle import restatement as R
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        params, heads, sched = cpu_models()
+        to = lambda d: {k: v.to(dev) for k, v in d.items()}
+        params, heads, sched = to(params), {k: to(v) for k, v in heads.items()}, to(sched)
+        obs = build_inputs(1)[:B].to(dev)
+        cfg = dict(epistemic_weight=0.1, pragmatic_weight=1.0, consistency_weight=0.1, discount_factor=0.99,
+                   preference_temperature=1.0)
+
+        def step():
+            with torch.no_grad():
+                zT = torch.randn(B, L, device=dev)
+                noise = [torch.randn(B, L, device=dev) for _ in range(T - 1)]
+                latent = R.generate_latent_trajectory(params, sched, zT, obs, noise)[-1]
+                nz = [dict(policy=torch.randn(B, A, device=dev), reparam=torch.randn(B, L, device=dev))
+                      for _ in range(K_TRAJ * HORIZON)]
+                return R.expected_free_energy(heads, cfg, latent, HORIZON, K_TRAJ, nz)[0]
+
+        step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return {"value": B / ms * 1e3, "unit": UNIT, "candidates": B, "ms": ms,
+            "what": "the reference's algorithm (oracle port) as eager PyTorch fp32, TF32 off, on this GPU"}
 
 
 def main():
@@ -343,6 +572,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE configs[2])")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary measurements of the N=1 line")
+    ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="with --impl reference: cuda = the oracle port as eager PyTorch fp32 on this box's GPU")
     ap.add_argument("--ref-candidates", type=int, default=CANDIDATES)

@@ -88,6 +88,9 @@ void aid_reset_launch_count(void);
  * aid_profile_collect synchronises on the recorded events and returns their summed duration. */
 int32_t aid_profile_select(int32_t epi, int32_t k, int32_t n);
 int32_t aid_profile_collect(double* total_ms_host, int64_t* launches_host);
+/* the same with up to 4 independent selections (slot 0 = the pair above) */
+int32_t aid_profile_select_slot(int32_t slot, int32_t epi, int32_t k, int32_t n);
+int32_t aid_profile_collect_slot(int32_t slot, double* total_ms_host, int64_t* launches_host);
 
 /* ---- weights ------------------------------------------------------------------------------
  * Derived cache of LatentScoreNetwork parameters: 16-bit tcgen05 operand tiles (128 rows x 64
