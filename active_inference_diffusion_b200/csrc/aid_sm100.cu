@@ -400,7 +400,12 @@ static int launch_gemm_lnact(const uint8_t* A, int row_tiles, const PLin& w, Epi
 // in its first form it is slower than the two separate kernels (3.65 vs 3.15 ms per denoise step at
 // 65,536 rows): the two epilogues in one kernel spill at 168 registers and phase 1 has only three
 // k-blocks of operands in flight.  Kept as the starting point of the cross-layer fusion work.
-static bool use_chain() {
+// AID_CHAIN=1 opts in.  Measured (round 2) also for the launch-latency-bound small batches, where
+// removing 13 of a step's 47 launches looked attractive: B <= 4,096 rows took 34.7 ms per 50-step call with
+// the chain kernel against 19.5 ms without -- a chain unit is a whole row-tile pair, so one CTA pair walks
+// all column groups of both layers serially, while the separate kernels spread them over the SMs.
+static bool use_chain(int row_tiles) {
+  (void)row_tiles;
   static const bool on = use_pairs() && getenv("AID_CHAIN") && atoi(getenv("AID_CHAIN")) != 0;
   return on;
 }
@@ -425,8 +430,8 @@ static int launch_chain_inst(const ChainArgs& ca, const EpiArgs& e1, const EpiAr
 }
 
 // mod: adaLN modulation weight (MODLN row map), w2: the layer that consumes the normalised tile
-static bool chain_ok(const PLin& mod, const PLin& w2) {
-  return use_chain() && mod.nw == 1 && w2.nw == 1 && mod.kb <= MAX_RES_KB && mod.kb % 2 == 0 &&
+static bool chain_ok(const PLin& mod, const PLin& w2, int row_tiles) {
+  return use_chain(row_tiles) && mod.nw == 1 && w2.nw == 1 && mod.kb <= MAX_RES_KB && mod.kb % 2 == 0 &&
          mod.n_tiles == mod.kb && w2.kb == mod.kb && w2.n_tiles % 2 == 0;
 }
 
@@ -777,7 +782,7 @@ static int run_score_trunk(const ScoreW& s, ScoreWS& w, const StepOut& o, cudaSt
   AID_TRY(f32_out(s.lp, zp, false));
   for (int i = 0; i < s.NB; ++i) {
     const ScoreBlockW& b = s.blk[i];
-    if (chain_ok(b.mod1, b.attn)) {
+    if (chain_ok(b.mod1, b.attn, w.RT)) {
       AID_TRY(launch_chain<EPI_F32>(cs, w.RT, b.mod1, b.attn, modln_args(), f32_args(true), st, w.err));
     } else {
       AID_TRY(modln(b.mod1));
@@ -785,7 +790,7 @@ static int run_score_trunk(const ScoreW& s, ScoreWS& w, const StepOut& o, cudaSt
     }
     EpiArgs e = epi_zero();
     e.act = ACT_GELU; e.n_valid = 4 * H; e.rows_valid = w.B; e.out_packed = w.act; e.out_kb = 4 * H / 64;
-    if (chain_ok(b.mod2, b.fc1)) {
+    if (chain_ok(b.mod2, b.fc1, w.RT)) {
       AID_TRY(launch_chain<EPI_PACK>(cs, w.RT, b.mod2, b.fc1, modln_args(), e, st, w.err));
     } else {
       AID_TRY(modln(b.mod2));
@@ -795,7 +800,7 @@ static int run_score_trunk(const ScoreW& s, ScoreWS& w, const StepOut& o, cudaSt
   }
   EpiArgs e = epi_zero();
   e.act = ACT_SILU; e.n_valid = H / 2; e.rows_valid = w.B; e.out_packed = w.o1; e.out_kb = ceil_div(H / 2, 64);
-  if (chain_ok(s.nf, s.out0)) {
+  if (chain_ok(s.nf, s.out0, w.RT)) {
     AID_TRY(launch_chain<EPI_PACK>(cs, w.RT, s.nf, s.out0, modln_args(), e, st, w.err));
   } else {
     AID_TRY(modln(s.nf));

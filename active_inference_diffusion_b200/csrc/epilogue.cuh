@@ -82,6 +82,36 @@ __device__ __forceinline__ void unpack_op16x8(const uint4 v, float* out) {
   }
 }
 
+// value, first and second derivative of the activation on a register pair
+template <int ACT>
+__device__ __forceinline__ void dact_eval2(const float2 x, float2& f, float2& d1, float2& d2) {
+  if constexpr (ACT == ACT_GELU) {
+    // erf in the Abramowitz-Stegun 7.1.26 form (see gelu_parts), all polynomial work as FFMA2
+    const float2 y = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752f, 0.70710678118654752f));
+    const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), y, make_float2(1.0f, 1.0f));
+    const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+    // 0.5 * (a1 + a2 t + a3 t^2 + a4 t^3 + a5 t^4): the 0.5 of Phi = 1 - q/2 folded into the coefficients
+    float2 p = __ffma2_rn(make_float2(0.5307027145f, 0.5307027145f), t, make_float2(-0.7265760135f, -0.7265760135f));
+    p = __ffma2_rn(p, t, make_float2(0.7107068705f, 0.7107068705f));
+    p = __ffma2_rn(p, t, make_float2(-0.142248368f, -0.142248368f));
+    p = __ffma2_rn(p, t, make_float2(0.127414796f, 0.127414796f));
+    const float2 y2 = __fmul2_rn(y, y);
+    float2 ex;
+    ex.x = ex2_approx(-1.4426950408889634f * y2.x);
+    ex.y = ex2_approx(-1.4426950408889634f * y2.y);
+    const float2 hq = __fmul2_rn(__fmul2_rn(p, t), ex);
+    const float2 Phi = make_float2(x.x < 0.f ? hq.x : 1.0f - hq.x, x.y < 0.f ? hq.y : 1.0f - hq.y);
+    const float2 phi = __fmul2_rn(ex, make_float2(0.3989422804014327f, 0.3989422804014327f));
+    f = __fmul2_rn(x, Phi);
+    d1 = __ffma2_rn(x, phi, Phi);
+    d2 = __fmul2_rn(phi, __ffma2_rn(make_float2(-x.x, -x.y), x, make_float2(2.0f, 2.0f)));
+  } else {
+    f = make_float2(dact_f<ACT>(x.x), dact_f<ACT>(x.y));
+    d1 = make_float2(dact_d1<ACT>(x.x), dact_d1<ACT>(x.y));
+    d2 = make_float2(dact_d2<ACT>(x.x), dact_d2<ACT>(x.y));
+  }
+}
+
 template <int EPI>
 struct EpiState {
   float bias;        // bias[nt*128 + r] of the tile about to be processed
@@ -161,8 +191,27 @@ __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
 // only; measured SLOWER on B200 (mlp.0 epilogue compute 92 us vs 72 us: the FMA pipe, not the XU
 // pipe, becomes the bound), kept as an accuracy option.  -DAID_EXACT_GELU: libm erff.
 __device__ __forceinline__ void act_gelu2(float& a, float& b) {
-#if defined(AID_EXACT_GELU) || defined(AID_F16)
+#if defined(AID_EXACT_GELU)
   a = act_gelu(a); b = act_gelu(b);
+#elif defined(AID_F16)
+  // fp16-operand builds (rel-1e-3 mode): Phi from erfc(t) = 2^(t Q(t)), t = |x|/sqrt2 <= 4.3, Q of degree 5
+  // (weighted least-squares fit of log2 erfc; |erfc error| <= 5e-7 evaluated in fp32): ONE MUFU
+  // operation per element like the tanh form of the bf16 build, erf-accurate.  For x < 0 the
+  // result is x * erfc/2 directly (no cancellation in the tail).
+  const float2 x = make_float2(a, b);
+  const float2 t = make_float2(fminf(fabsf(a) * 0.70710678118654752f, 4.3f), fminf(fabsf(b) * 0.70710678118654752f, 4.3f));
+#define AID_C2(v) make_float2(v, v)
+  float2 q = __ffma2_rn(t, AID_C2(0.00024000316524137267f), AID_C2(-0.004126049044898346f));
+  q = __ffma2_rn(q, t, AID_C2(0.031667067247158676f));
+  q = __ffma2_rn(q, t, AID_C2(-0.15025340151855682f));
+  q = __ffma2_rn(q, t, AID_C2(-0.9180013625978741f));
+  q = __ffma2_rn(q, t, AID_C2(-1.6279399503718077f));
+#undef AID_C2
+  const float2 pw = __fmul2_rn(q, t);
+  const float h0 = 0.5f * ex2_approx(pw.x), h1 = 0.5f * ex2_approx(pw.y);
+  const float2 Phi = make_float2(a < 0.f ? h0 : 1.0f - h0, b < 0.f ? h1 : 1.0f - h1);
+  const float2 r = __fmul2_rn(x, Phi);
+  a = r.x; b = r.y;
 #elif !defined(AID_GELU_POLY)
   const float2 x = make_float2(a, b);
   const float2 p = __ffma2_rn(__fmul2_rn(x, x), make_float2(0.0356774081f, 0.0356774081f),
@@ -511,83 +560,93 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
       st.rt = rt2;
     }
   } else if constexpr (EPI == EPI_DACT) {
-    // Training epilogues (train.inc).  One thread = one row; 32 columns per chunk.
+    // Training epilogues (train.inc).  One thread = one row; a 32-column accumulator chunk is consumed
+    // in four 8-column pieces (= one 16-byte packed store each), so that only the raw chunk and one
+    // piece of operands are live: the first version kept four 32-element arrays and spilled.  The
+    // activation derivatives are evaluated on register pairs (dact_eval2: packed fp32x2 FMA pipe; the
+    // two MUFU operations per element are what bounds these kernels).
     const int srt = rt % e.src_rt;                       // row tile of the saved forward tensors
     const bool first_half = rt < e.src_rt;
     const float aux_scale = e.aux_scale ? __ldg(e.aux_scale) : 1.0f;
-    uint32_t raw[32];
-    tmem_ld32(tmem_tile, raw);
+    const int mode = e.dact_mode;
+    const bool use_aux = mode == DACT_HAT || (mode == DACT_BWD && first_half && e.aux_in != nullptr);
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       const int n0 = nt * TILE_N + c * 32;
       const int kb_out = n0 >> 6;
       const bool in_range = kb_out < e.out_kb;           // uniform over the group
-      float pre[32];
-      uint4 ax[4];
-      if (e.dact_mode != DACT_FWD && in_range) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 v = e.pre_tiled[((size_t)srt * e.pre_ld4 + (n0 >> 2) + q) * TILE_M + r];
-          pre[q * 4 + 0] = v.x; pre[q * 4 + 1] = v.y; pre[q * 4 + 2] = v.z; pre[q * 4 + 3] = v.w;
-        }
-        if (e.dact_mode == DACT_HAT || (e.dact_mode == DACT_BWD && first_half && e.aux_in)) {
-          const __nv_bfloat16* at = e.aux_in + (size_t)(srt * e.out_kb + kb_out) * TILE_ELEMS;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            ax[q] = *reinterpret_cast<const uint4*>(at + (((n0 & 63) >> 3) + q) * (TILE_M * 8) + r * 8);
-        }
-      }
-      float y[32];
-      if (e.dact_mode == DACT_FWD) bias32_from_smem(sb, c * 32, y);
+      uint32_t raw[32];
+      tmem_ld32(tmem_tile + c * 32, raw);
+      float b32[32];
+      if (mode == DACT_FWD) bias32_from_smem(sb, c * 32, b32);
       tmem_ld_wait();
-      if (e.dact_mode == DACT_FWD) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(raw[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(raw[j]);
-      }
-      if (c + 1 < 4) tmem_ld32(tmem_tile + (c + 1) * 32, raw);
-      else acc_release(rel);
+      if (c == 3) acc_release(rel);                      // the whole tile is in registers
       if (!in_range) continue;
       __nv_bfloat16* tile = e.out_packed + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
-      if (e.dact_mode == DACT_FWD) {
+      const int chunk0 = (n0 & 63) >> 3;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = (n0 + j < e.n_valid) ? y[j] : 0.f;
+      for (int q = 0; q < 4; ++q) {
+        const int col = n0 + q * 8;
+        float y[8], o[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          e.pre_tiled[((size_t)rt * e.pre_ld4 + (n0 >> 2) + q) * TILE_M + r] =
-              make_float4(y[q * 4 + 0], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+        for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(raw[q * 8 + i]);
+        const size_t packed_at = (size_t)(chunk0 + q) * (TILE_M * 8) + r * 8;
+        if (mode == DACT_FWD) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = dact_f<ACT>(y[j]);
-        store_packed32(tile, r, n0 & 63, y);
-      } else {
-        if (e.dact_mode == DACT_VJP && e.aux_out) {
-          __nv_bfloat16* at = e.aux_out + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
-          store_packed32(at, r, n0 & 63, y);
+          for (int i = 0; i < 8; ++i) y[i] = (col + i < e.n_valid) ? y[i] + b32[q * 8 + i] : 0.f;
+          float4* pp = e.pre_tiled + ((size_t)rt * e.pre_ld4 + (col >> 2)) * TILE_M + r;
+          pp[0] = make_float4(y[0], y[1], y[2], y[3]);
+          pp[TILE_M] = make_float4(y[4], y[5], y[6], y[7]);
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            float2 f, d1, d2;
+            dact_eval2<ACT>(make_float2(y[i], y[i + 1]), f, d1, d2);
+            o[i] = f.x; o[i + 1] = f.y;
+          }
+        } else {
+          const float4* pp = e.pre_tiled + ((size_t)srt * e.pre_ld4 + (col >> 2)) * TILE_M + r;
+          const float4 p0 = pp[0], p1 = pp[TILE_M];
+          const float pre[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+          float ax[8];
+          if (use_aux) {
+            const uint4 av = *reinterpret_cast<const uint4*>(e.aux_in + (size_t)(srt * e.out_kb + kb_out) * TILE_ELEMS + packed_at);
+            unpack_op16x8(av, ax);
+          }
+          if (mode == DACT_VJP && e.aux_out) {
+            uint4 v;
+            v.x = pack_op16x2(y[0], y[1]); v.y = pack_op16x2(y[2], y[3]);
+            v.z = pack_op16x2(y[4], y[5]); v.w = pack_op16x2(y[6], y[7]);
+            *reinterpret_cast<uint4*>(e.aux_out + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS + packed_at) = v;
+          }
+          float g2[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            float2 f, d1, d2;
+            dact_eval2<ACT>(make_float2(pre[i], pre[i + 1]), f, d1, d2);
+            const float2 acc = make_float2(y[i], y[i + 1]);
+            float2 out = __fmul2_rn(acc, d1);
+            if (mode == DACT_HAT) {
+              const float2 t2 = __fmul2_rn(__fmul2_rn(acc, make_float2(ax[i], ax[i + 1])),
+                                           __fmul2_rn(d2, make_float2(aux_scale, aux_scale)));
+              g2[i] = (col + i < e.n_valid) ? t2.x : 0.f;
+              g2[i + 1] = (col + i + 1 < e.n_valid) ? t2.y : 0.f;
+            } else if (mode == DACT_BWD && use_aux) {
+              out = __fadd2_rn(out, make_float2(ax[i], ax[i + 1]));
+            }
+            o[i] = (col + i < e.n_valid) ? out.x : 0.f;
+            o[i + 1] = (col + i + 1 < e.n_valid) ? out.y : 0.f;
+          }
+          if (mode == DACT_HAT) {
+            uint4 v;
+            v.x = pack_op16x2(g2[0], g2[1]); v.y = pack_op16x2(g2[2], g2[3]);
+            v.z = pack_op16x2(g2[4], g2[5]); v.w = pack_op16x2(g2[6], g2[7]);
+            *reinterpret_cast<uint4*>(e.aux_out + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS + packed_at) = v;
+          }
         }
-        float g2[32];
-        if (e.dact_mode == DACT_HAT) {
-          float cv[32];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) unpack_op16x8(ax[q], cv + q * 8);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) g2[j] = (n0 + j < e.n_valid) ? y[j] * cv[j] * dact_d2<ACT>(pre[j]) * aux_scale : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = (n0 + j < e.n_valid) ? y[j] * dact_d1<ACT>(pre[j]) : 0.f;
-        if (e.dact_mode == DACT_BWD && first_half && e.aux_in) {
-          float av[32];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) unpack_op16x8(ax[q], av + q * 8);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] += av[j];
-        }
-        store_packed32(tile, r, n0 & 63, y);
-        if (e.dact_mode == DACT_HAT) {
-          __nv_bfloat16* at = e.aux_out + (size_t)(rt * e.out_kb + kb_out) * TILE_ELEMS;
-          store_packed32(at, r, n0 & 63, g2);
-        }
+        uint4 v;
+        v.x = pack_op16x2(o[0], o[1]); v.y = pack_op16x2(o[2], o[3]);
+        v.z = pack_op16x2(o[4], o[5]); v.w = pack_op16x2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(tile + packed_at) = v;
       }
     }
   } else {  // EPI_SCORE

@@ -187,6 +187,17 @@ __device__ __forceinline__ int packed_off(int r, int c, int R = TILE_M) {
   return (c >> 3) * (R * 8) + r * 8 + (c & 7);
 }
 
+// bare MUFU operations (exp2f / __frcp_rn expand to multi-instruction sequences with range fix-ups)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
 // GELU.  The reference uses the exact erf form (nn.GELU(), models/score_networks.py:199).  The
 // epilogue budget is ~16 issue slots per output element (K=512), erff alone costs ~40, so the hot

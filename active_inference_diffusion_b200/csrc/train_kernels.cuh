@@ -219,6 +219,60 @@ __global__ void k_wgrad_reduce(const float* __restrict__ partial, int splits, si
 }
 
 // =================================================================================================
+// All weight packs of a step in ONE launch (the per-Linear launches were 134 tiny kernels, ~2 ms of a
+// 33 ms step): blockIdx.y selects a job, the job table travels as a kernel parameter.
+struct PackJob {
+  const float* src;
+  long long rs, cs;          // element (row, col) of the operand at src[row * rs + col * cs]
+  int rows, cols;
+  __nv_bfloat16* dst;
+  int row_tiles, kb_total, nw;
+};
+constexpr int PACK_JOBS = 64;
+struct PackJobs {
+  PackJob job[PACK_JOBS];
+};
+__global__ void __launch_bounds__(256) k_pack_multi(const PackJobs jobs) {
+  const PackJob j = jobs.job[blockIdx.y];
+  const size_t total = (size_t)j.row_tiles * j.kb_total * 1024;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    int rt, kb, r, ch;
+    chunk_coords(idx, j.kb_total, rt, kb, r, ch);
+    if (j.cs == 1) {            // row-major source: neighbouring lanes take neighbouring 32-byte pieces of one row
+      ch = (int)(idx & 7);
+      r = (int)((idx >> 3) & 127);
+    }
+    const int row = rt * TILE_M + r, c0 = kb * TILE_K + ch * 8;
+    float v[8];
+    if (j.cs == 1 && (j.rs & 3) == 0 && row < j.rows && c0 + 8 <= j.cols) {
+      const float4* p = reinterpret_cast<const float4*>(j.src + (long long)row * j.rs + c0);
+      const float4 a = __ldg(p), b = __ldg(p + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[i] = (row < j.rows && c0 + i < j.cols) ? __ldg(j.src + (long long)row * j.rs + (long long)(c0 + i) * j.cs) : 0.f;
+    }
+    store_chunk(j.dst, rt, kb, j.kb_total, r, ch, v, j.nw);
+  }
+}
+struct BiasJob {
+  const float* src;          // null: zeros
+  int n;
+  float* dst;
+  int n_pad;
+};
+struct BiasJobs {
+  BiasJob job[PACK_JOBS];
+};
+__global__ void __launch_bounds__(256) k_bias_multi(const BiasJobs jobs) {
+  const BiasJob j = jobs.job[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.n_pad; i += gridDim.x * blockDim.x)
+    j.dst[i] = (j.src && i < j.n) ? j.src[i] : 0.f;
+}
+
+// =================================================================================================
 // Column sums of a packed operand (bias gradients): out[n] (+)= scale * sum_rows pack[row, n].
 // grid = (feature blocks, row splits); block = 256 threads = 8 chunks x 32 row lanes.
 __global__ void k_colsum_packed(const __nv_bfloat16* __restrict__ pk, int kb_total, int row_tiles, int N,
@@ -620,26 +674,47 @@ __global__ void k_cscale(const float* __restrict__ mult, float* __restrict__ sca
   scale[3] = S;
   scale[4] = 1.0f / S;
 }
-__global__ void __launch_bounds__(1024) k_amax_scale(const float* __restrict__ a, size_t na, const float* __restrict__ a_mul,
-                                                     const float* __restrict__ b, size_t nb, float* __restrict__ scale) {
-  __shared__ float red[1024];
-  float m = 0.f;
-  for (size_t i = threadIdx.x; i < na; i += blockDim.x) m = fmaxf(m, fabsf(a[i]));
-  m *= fabsf(__ldg(a_mul));
-  if (b)
-    for (size_t i = threadIdx.x; i < nb; i += blockDim.x) m = fmaxf(m, fabsf(b[i]));
-  red[threadIdx.x] = m;
+// two stages: per-block maxima folded with atomicMax on the bit pattern (non-negative floats order like
+// unsigned integers) into scale[8] (a), scale[9] (b); then one thread derives the scales
+__global__ void __launch_bounds__(256) k_amax_partial(const float* __restrict__ a, size_t na, const float* __restrict__ b,
+                                                      size_t nb, float* __restrict__ scale) {
+  __shared__ float red[2][256];
+  float ma = 0.f, mb = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = i0; i < (na >> 2); i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(a)[i];
+    ma = fmaxf(ma, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  for (size_t i = (na & ~(size_t)3) + i0; i < na; i += stride) ma = fmaxf(ma, fabsf(a[i]));
+  if (b) {
+    for (size_t i = i0; i < (nb >> 2); i += stride) {
+      const float4 v = reinterpret_cast<const float4*>(b)[i];
+      mb = fmaxf(mb, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (size_t i = (nb & ~(size_t)3) + i0; i < nb; i += stride) mb = fmaxf(mb, fabsf(b[i]));
+  }
+  red[0][threadIdx.x] = ma;
+  red[1][threadIdx.x] = mb;
   __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      red[0][threadIdx.x] = fmaxf(red[0][threadIdx.x], red[0][threadIdx.x + o]);
+      red[1][threadIdx.x] = fmaxf(red[1][threadIdx.x], red[1][threadIdx.x + o]);
+    }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const float S = pow2_scale(red[0], 6);
-    scale[0] = S;
-    scale[1] = 1.0f / S;
-    scale[2] = 1.0f / (S * scale[3]);
+    atomicMax(reinterpret_cast<unsigned int*>(scale + 8), __float_as_uint(red[0][0]));
+    atomicMax(reinterpret_cast<unsigned int*>(scale + 9), __float_as_uint(red[1][0]));
   }
+}
+__global__ void k_amax_finish(const float* __restrict__ a_mul, float* __restrict__ scale) {
+  if (threadIdx.x != 0) return;
+  const float m = fmaxf(scale[8] * fabsf(__ldg(a_mul)), scale[9]);
+  const float S = pow2_scale(m, 6);
+  scale[0] = S;
+  scale[1] = 1.0f / S;
+  scale[2] = 1.0f / (S * scale[3]);
 }
 
 // out[i] = in[i] * mul * (*mul_dev)

@@ -7,10 +7,11 @@ for row in csv.DictReader(lines):
     v = float(row["Metric Value"].replace(",", ""))
     unit = row["Metric Unit"]
     v = v / 1e3 if unit in ("ns", "nsecond") else (v * 1e3 if unit in ("ms", "msecond") else v)
-    key = name.split("(")[0][-44:]
+    key = re.sub(r"^.*aid::", "", name.split("(")[0])[:60] if "aid::" in name else name.split("(")[0][-60:]
     agg[key][0] += 1
     agg[key][1] += v
 tot = sum(v[1] for v in agg.values())
 print(f"launches {sum(v[0] for v in agg.values())}  total {tot:.1f} us")
-for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:16]:
-    print(f"{k:46s} n={c:5d} total={t:10.1f}us avg={t / c:8.1f}us share={t / tot * 100:5.1f}%")
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 24
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+    print(f"{k:62s} n={c:5d} total={t:10.1f}us avg={t / c:8.1f}us share={t / tot * 100:5.1f}%")
