@@ -112,6 +112,18 @@ class FunctionSpaceEpistemicEstimator(nn.Module):
         marg = torch.cat([jac[i * B:(i + 1) * B][torch.randperm(B, device=jac.device) if perms is None else perms[i]]
                           for i in range(num_samples)], dim=0)
         t_marg = autograd_path.seq(self.mine_network, torch.cat([marg, lat], dim=1))
+        group = getattr(self, "data_parallel_group", None)
+        if group is not None and not torch.is_grad_enabled():
+            # rows sharded over ranks: the statistic of the GLOBAL batch from one 3-float all-reduce
+            mi, joint, marginal_term, t_exp = distributed.sharded_mine_statistic(t_joint, t_marg, group)
+            if float(self.running_mean) == 0:
+                self.running_mean = t_exp.reshape(())
+            else:
+                self.running_mean = (self.alpha * t_exp + (1.0 - self.alpha) * self.running_mean).reshape(())
+            metrics = {"epistemic/mi_estimate": mi.item(), "epistemic/joint_term": joint.item(),
+                       "epistemic/marginal_term": marginal_term.item(),
+                       "epistemic/running_mean": float(self.running_mean)}
+            return torch.clamp(mi.expand(B), min=0.0), metrics
         # ema_loss (:828-836): forward value log(mean(exp(T))), running mean updated on the side
         t_exp = torch.exp(torch.logsumexp(t_marg, 0) - math.log(t_marg.shape[0])).detach()
         if float(self.running_mean) == 0:
@@ -318,6 +330,30 @@ class DiffusionActiveInference(nn.Module):
                     vals.append(e[0])
                     cur = mean + reparam_noise[d] * std
         return torch.stack(vals), metrics
+
+    # set by the agent: `agent.active_inference.epistemic_optimizer = Adam(...)` (agents/base_agent.py:134-139)
+    epistemic_optimizer = None
+
+    def train_epistemic_estimator(self, latents: torch.Tensor, actions: torch.Tensor, next_latents: torch.Tensor,
+                                  **draws):
+        """One MINE training step (core/active_inference.py:420-445, called by the agents every 5th
+        `train_step`, agents/state_agent.py:217-220): loss = -mean(MI estimate) on the predicted
+        next-latent distribution, gradient clipping at `config.gradient_clip`, one optimizer step.
+        `next_latents` is accepted and unused, as in the reference.  Returns (mi, metrics).  Keyword
+        arguments are forwarded to the estimator (parity tests inject its draws)."""
+        if self.epistemic_optimizer is None:
+            raise RuntimeError("train_epistemic_estimator: set `epistemic_optimizer` first (the reference's agents "
+                               "assign it, agents/base_agent.py:134-139)")
+        latents, actions = latents.to(self.device), actions.to(self.device)
+        next_mean, next_logvar = self.predict_next_latent(latents, actions)
+        mi_estimate, metrics = self.epistemic_estimator(next_mean, next_logvar, **draws)
+        loss = -mi_estimate.mean()
+        self.epistemic_optimizer.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.epistemic_estimator.parameters(), self.config.gradient_clip)
+        self.epistemic_optimizer.step()
+        self._heads.invalidate_packed()         # the dynamics head may be among the optimised parameters
+        return mi_estimate.mean().item(), metrics
 
     def compute_epistemic_value(self, next_latent_mean, next_latent_logvar, num_samples: int = 5):
         with torch.no_grad():

@@ -560,23 +560,43 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
       st.rt = rt2;
     }
   } else if constexpr (EPI == EPI_DACT) {
-    // Training epilogues (train.inc).  One thread = one row; a 32-column accumulator chunk is consumed
-    // in four 8-column pieces (= one 16-byte packed store each), so that only the raw chunk and one
-    // piece of operands are live: the first version kept four 32-element arrays and spilled.  The
-    // activation derivatives are evaluated on register pairs (dact_eval2: packed fp32x2 FMA pipe; the
-    // two MUFU operations per element are what bounds these kernels).
+    // Training epilogues (train.inc).  One thread = one row.  Per 32-column accumulator chunk the saved
+    // pre-activation (8 float4) and the auxiliary packed operand (4 x 16 B) come from HBM: they are
+    // fetched one chunk AHEAD into a second register set (the first version loaded them right before
+    // use and the backward modes ran 2.5x slower than the forward mode: exposed load latency with only
+    // eight epilogue warps per SM).  The math consumes a chunk in four 8-column pieces (= one 16-byte
+    // packed store each); activation derivatives are evaluated on register pairs (dact_eval2).
     const int srt = rt % e.src_rt;                       // row tile of the saved forward tensors
     const bool first_half = rt < e.src_rt;
     const float aux_scale = e.aux_scale ? __ldg(e.aux_scale) : 1.0f;
     const int mode = e.dact_mode;
     const bool use_aux = mode == DACT_HAT || (mode == DACT_BWD && first_half && e.aux_in != nullptr);
-#pragma unroll 1
+    const bool rd_pre = mode != DACT_FWD;
+    float4 pre[2][8];
+    uint4 aux[2][4];
+    auto fetch = [&](int c, int buf) {
+      const int n0 = nt * TILE_N + c * 32;
+      if ((n0 >> 6) >= e.out_kb) return;
+      if (rd_pre) {
+        const float4* pp = e.pre_tiled + ((size_t)srt * e.pre_ld4 + (n0 >> 2)) * TILE_M + r;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pre[buf][q] = pp[(size_t)q * TILE_M];
+      }
+      if (use_aux) {
+        const __nv_bfloat16* at = e.aux_in + (size_t)(srt * e.out_kb + (n0 >> 6)) * TILE_ELEMS + (size_t)((n0 & 63) >> 3) * (TILE_M * 8) + r * 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) aux[buf][q] = *reinterpret_cast<const uint4*>(at + (size_t)q * (TILE_M * 8));
+      }
+    };
+    fetch(0, 0);
+#pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int n0 = nt * TILE_N + c * 32;
       const int kb_out = n0 >> 6;
       const bool in_range = kb_out < e.out_kb;           // uniform over the group
       uint32_t raw[32];
       tmem_ld32(tmem_tile + c * 32, raw);
+      if (c + 1 < 4) fetch(c + 1, (c + 1) & 1);          // next chunk's operands fly during this chunk's math
       float b32[32];
       if (mode == DACT_FWD) bias32_from_smem(sb, c * 32, b32);
       tmem_ld_wait();
@@ -604,14 +624,10 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
             o[i] = f.x; o[i + 1] = f.y;
           }
         } else {
-          const float4* pp = e.pre_tiled + ((size_t)srt * e.pre_ld4 + (col >> 2)) * TILE_M + r;
-          const float4 p0 = pp[0], p1 = pp[TILE_M];
-          const float pre[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+          const float4 p0 = pre[c & 1][q * 2], p1 = pre[c & 1][q * 2 + 1];
+          const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
           float ax[8];
-          if (use_aux) {
-            const uint4 av = *reinterpret_cast<const uint4*>(e.aux_in + (size_t)(srt * e.out_kb + kb_out) * TILE_ELEMS + packed_at);
-            unpack_op16x8(av, ax);
-          }
+          if (use_aux) unpack_op16x8(aux[c & 1][q], ax);
           if (mode == DACT_VJP && e.aux_out) {
             uint4 v;
             v.x = pack_op16x2(y[0], y[1]); v.y = pack_op16x2(y[2], y[3]);
@@ -622,7 +638,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, uint32_t tmem_tile,
 #pragma unroll
           for (int i = 0; i < 8; i += 2) {
             float2 f, d1, d2;
-            dact_eval2<ACT>(make_float2(pre[i], pre[i + 1]), f, d1, d2);
+            dact_eval2<ACT>(make_float2(pv[i], pv[i + 1]), f, d1, d2);
             const float2 acc = make_float2(y[i], y[i + 1]);
             float2 out = __fmul2_rn(acc, d1);
             if (mode == DACT_HAT) {

@@ -106,6 +106,22 @@ def gather_time_loss(t: torch.Tensor, loss: torch.Tensor, group=None) -> Tuple[t
     return out[:, 0].contiguous(), out[:, 1].contiguous()
 
 
+def sharded_mine_statistic(t_joint: torch.Tensor, t_marg: torch.Tensor, group=None):
+    """MINE statistic of a batch sharded over ranks (core/active_inference.py:1040-1053 is
+    a batch-GLOBAL mean): every rank contributes (sum T_joint, sum exp(T_marg), count) and ONE 3-float
+    all-reduce gives all ranks the statistic of the global batch:
+        joint = sum T_joint / n,  t_exp = sum exp(T_marg) / n,  mi = joint - log(t_exp).
+    Returns (mi, joint, log t_exp, t_exp) as 0-dim tensors.  The marginal permutation stays inside a
+    rank's shard (documented deviation from the single-process randperm over the whole batch)."""
+    stat = torch.stack([t_joint.detach().double().sum(), t_marg.detach().double().exp().sum(),
+                        torch.tensor(float(t_joint.numel()), dtype=torch.float64, device=t_joint.device)])
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stat, group=group)
+    joint = stat[0] / stat[2]
+    t_exp = stat[1] / stat[2]
+    return (joint - t_exp.log()).float(), joint.float(), t_exp.log().float(), t_exp.float()
+
+
 def allreduce_grads(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20, group=None) -> None:
     """Average the gradients of `params` over ranks.  Gradients that already live in one contiguous
     buffer (FlatGrads) go out as one collective; others are exchanged tensor by tensor, largest first

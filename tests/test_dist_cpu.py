@@ -88,7 +88,13 @@ def _worker_plumbing(rank, world, port, q):
     (lin(x) ** 2).mean().backward()
     assert lin.weight.grad.data_ptr() == fg.views[0].data_ptr()      # accumulated in place, still a view
     fg.allreduce()
-    q.put((rank, torch.equal(tg, t_all) and torch.equal(lg, loss_all), w, float(t_mean), fg.flat.clone()))
+    # sharded MINE statistic: one 3-float all-reduce = the statistic of the concatenated batch
+    from active_inference_diffusion_b200.distributed import sharded_mine_statistic
+    gj = torch.Generator().manual_seed(9)
+    tj_all, tm_all = torch.randn(world * 40, 1, generator=gj), torch.randn(world * 40, 1, generator=gj)
+    mi, joint, marg, t_exp = sharded_mine_statistic(tj_all[rank * 40:(rank + 1) * 40], tm_all[rank * 40:(rank + 1) * 40])
+    q.put((rank, torch.equal(tg, t_all) and torch.equal(lg, loss_all), w, float(t_mean), fg.flat.clone(),
+           (float(mi), float(joint), float(marg))))
     dist.destroy_process_group()
 
 
@@ -117,7 +123,12 @@ def test_two_rank_training_plumbing_time_importance_gather_scalar_mean_flat_grad
     x = torch.randn(world * 16, 5, generator=torch.Generator().manual_seed(2))
     (lin(x) ** 2).mean().backward()
     want = torch.cat([lin.weight.grad.reshape(-1), lin.bias.grad.reshape(-1)])
-    for rank, gathered_ok, w, t_mean, flat in out:
+    gj = torch.Generator().manual_seed(9)
+    tj_all, tm_all = torch.randn(world * 40, 1, generator=gj), torch.randn(world * 40, 1, generator=gj)
+    marg_want = float(tm_all.double().exp().mean().log())
+    for rank, gathered_ok, w, t_mean, flat, mine in out:
+        assert abs(mine[1] - float(tj_all.mean())) < 1e-6 and abs(mine[2] - marg_want) < 1e-6
+        assert abs(mine[0] - (float(tj_all.mean()) - marg_want)) < 1e-6
         assert gathered_ok
         assert torch.equal(w, w_want)                      # bit-identical EMA on every rank
         assert abs(t_mean - float(t_all.mean())) < 1e-6

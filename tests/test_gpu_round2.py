@@ -415,3 +415,82 @@ def test_packed_cache_invalidation_after_data_edits():
         sd["output_proj.2.weight"] *= 0.5
         net.load_state_dict(sd)
         assert torch.equal(net(z, t, obs), base)
+
+
+# ---------------------------------------------------------------------------------------------
+# train_epistemic_estimator (the reference's agents call it every 5th train_step)
+def test_train_epistemic_estimator_step_matches_oracle_gradient():
+    """core/active_inference.py:420-445: loss = -mean(MI), clip at config.gradient_clip, optimizer step.
+    With plain SGD (lr 1) the parameter change IS the clipped gradient; compared with autograd on the
+    oracle restatement fed the same draws (first call: running mean 0, where the MINE EMA gradient equals
+    the plain gradient of log-mean-exp up to its 1e-6 stabiliser)."""
+    from oracle.harness import perturb_generic
+    L, A, H, B, S = 32, 6, 128, 48, 3
+    ai, nets, cfg = make_ai(L, A, H)
+    est = ai.epistemic_estimator
+    own = {k: v.detach().cpu() for k, v in est.state_dict().items()
+           if not k.startswith("decoder.") and k not in ("perturbation_scale", "running_mean")}
+    est.load_state_dict(perturb_generic(own, 9, 0.05), strict=False)
+    with pytest.raises(RuntimeError, match="epistemic_optimizer"):
+        ai.train_epistemic_estimator(torch.zeros(B, L).cuda(), torch.zeros(B, A).cuda(), torch.zeros(B, L).cuda())
+    names = [k for k, _ in est.named_parameters() if not k.startswith("decoder.")]
+    params = [p for k, p in est.named_parameters() if not k.startswith("decoder.")]
+    ai.epistemic_optimizer = torch.optim.SGD(params, lr=1.0)
+    before = [p.detach().clone() for p in params]
+    g = gen(78)
+    lat, act = torch.randn(B, L, generator=g), torch.randn(B, A, generator=g)
+    z_eps = [torch.randn(B, L, generator=g) for _ in range(S)]
+    dir_eps = [torch.randn(S * B, L, generator=g) for _ in range(4)]
+    perms = [torch.randperm(B, generator=g) for _ in range(S)]
+    mi, metrics = ai.train_epistemic_estimator(lat.cuda(), act.cuda(), lat.cuda(), num_samples=S,
+                                               z_noise=[e.cuda() for e in z_eps], dir_noise=[e.cuda() for e in dir_eps],
+                                               perms=[p.cuda() for p in perms])
+    step = {k: (b - p.detach()).cpu() for k, b, p in zip(names, before, params)}
+    # oracle: same draws, autograd
+    ep = {k: v.detach().cpu().clone() for k, v in zip(names, before)}
+    ep = {k: v.requires_grad_(True) for k, v in ep.items()}
+    ep["perturbation_scale"] = est.perturbation_scale.detach().cpu()
+    mean, logvar = R.predict_next_latent(nets["dynamics"], lat, act)
+    want, wmi, _, _, _ = R.epistemic_value(ep, nets["decoder"], mean, logvar, z_eps, dir_eps, perms, 0.0)
+    (-want.mean()).backward()
+    assert abs(mi - float(want.mean())) < 2e-3
+    grads = {k: ep[k].grad for k in names if ep[k].grad is not None}
+    total = torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values()))
+    clip = min(1.0, float(cfg.gradient_clip) / (float(total) + 1e-6))
+    checked = 0
+    for k, gr in grads.items():
+        if float(gr.abs().max()) == 0.0:
+            assert float(step[k].abs().max()) < 1e-7
+            continue
+        assert rel_l2(step[k], gr * clip) < 5e-3, (k, rel_l2(step[k], gr * clip))
+        checked += 1
+    assert checked >= 8 or float(wmi) <= 0.0
+
+
+def test_batched_belief_update_equals_separate_calls():
+    """train_utils.update_belief_batched: the three diffusion runs of a training step as one call; with
+    the in-kernel Philox stream addressed by global row, each set's latents equal what a separate call
+    would draw for those rows."""
+    from active_inference_diffusion_b200 import update_belief_batched
+    L, A, H, T, B = 32, 6, 128, 6, 70
+    ai, nets, _ = make_ai(L, A, H, T)
+    dev = torch.device("cuda", 0)
+    d = ai.latent_diffusion
+    d.noise_source = "philox"
+    g = gen(3)
+    obs, nxt = torch.randn(B, L, generator=g).cuda(), torch.randn(B, L, generator=g).cuda()
+    d.seed_philox(9, dev)
+    infos = update_belief_batched(ai, [obs, nxt, nxt])
+    assert [tuple(i["latent"].shape) for i in infos] == [(B, L)] * 3
+    # separate calls over the same global rows of the same noise stream call
+    outs = []
+    for k, o in enumerate([obs, nxt, nxt]):
+        d.seed_philox(9, dev)
+        d.row_offset = k * B
+        outs.append(ai.update_belief_via_diffusion(o)["latent"])
+    d.row_offset = 0
+    for a, b in zip(infos, outs):
+        assert torch.equal(a["latent"], b)
+    assert not torch.equal(infos[1]["latent"], infos[2]["latent"])      # same observations, independent noise rows
+    rec = torch.nn.functional.mse_loss(ai.decode_observation(outs[0]), obs)
+    assert abs(float(infos[0]["reconstruction_error"]) - float(rec)) < 1e-6 * (1 + float(rec))

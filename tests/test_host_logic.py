@@ -190,3 +190,33 @@ def test_graphed_step_and_colsum_fail_loudly_without_cuda():
     with pytest.raises(RuntimeError):
         _lib.gelu_double_backward(torch.zeros(4), torch.zeros(4), torch.zeros(4))
     assert _lib.lib().aid_colsum_workspace_bytes(1000, 512) >= 512 * 4
+
+
+def test_device_running_mean_std_matches_reference_normaliser():
+    """train_utils.RunningMeanStd (device tensors, float64) == the reference's numpy RunningMeanStd
+    (agents/base_agent.py:24-52) update by update; runs on CPU tensors here, on the GPU in training."""
+    import numpy as np
+    from active_inference_diffusion_b200.train_utils import RunningMeanStd
+
+    class Ref:                                   # restated from agents/base_agent.py:24-52
+        def __init__(self, epsilon=1e-4):
+            self.mean, self.var, self.count = np.zeros(()), np.ones(()), epsilon
+
+        def update(self, x):
+            bm, bv, bc = np.mean(x, axis=0), np.var(x, axis=0), x.shape[0]
+            delta, tot = bm - self.mean, self.count + bc
+            m2 = self.var * self.count + bv * bc + np.square(delta) * self.count * bc / tot
+            self.mean, self.var, self.count = self.mean + delta * bc / tot, m2 / tot, tot
+
+        def normalize(self, x):
+            return (x - self.mean) / np.sqrt(self.var + 1e-8)
+
+    ours, ref = RunningMeanStd(device="cpu"), Ref()
+    g = torch.Generator().manual_seed(0)
+    for i in range(5):
+        r = torch.randn(256, generator=g) * (1 + i) + 0.3 * i
+        ours.update(r)
+        ref.update(r.double().numpy())
+        want = torch.tensor(ref.normalize(r.double().numpy()), dtype=torch.float32)
+        assert torch.allclose(ours.normalize(r), want, rtol=1e-6, atol=1e-6)
+    assert abs(float(ours.mean) - float(ref.mean)) < 1e-12 and abs(float(ours.var) - float(ref.var)) < 1e-12
