@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 #           rate: the rel-1e-3 ("fp32/TF32") contract of the sampled latents, EFE, losses, gradients
 LIB_PATHS = {"bf16": os.path.join(_HERE, "libaid_sm100.so"), "f16": os.path.join(_HERE, "libaid_sm100_f16.so")}
 LIB_PATH = LIB_PATHS["bf16"]
-ABI_VERSION = 2
+ABI_VERSION = 3
 OPERAND_TYPES = tuple(LIB_PATHS)
 _operand = os.environ.get("AID_PRECISION", "bf16")
 if _operand not in LIB_PATHS:
@@ -64,6 +64,11 @@ class AidScoreDims(ctypes.Structure):
 class AidHeadsDims(ctypes.Structure):
     _fields_ = [("latent_dim", c_int32), ("action_dim", c_int32), ("hidden_dim", c_int32),
                 ("time_embed_dim", c_int32)]
+
+
+class AidEpistemicDims(ctypes.Structure):
+    _fields_ = [("latent_dim", c_int32), ("hidden_dim", c_int32), ("observation_dim", c_int32),
+                ("jacobian_dim", c_int32)]
 
 
 class AidEncoderDims(ctypes.Structure):
@@ -219,6 +224,20 @@ def _declare_r2(l: ctypes.CDLL) -> None:
     l.aid_philox_normal.argtypes = [c_void_p, ctypes.c_uint32, c_int64, c_void_p, c_int32, c_int32, c_void_p]
 
 
+def _declare_epistemic(l: ctypes.CDLL) -> None:
+    D = POINTER(AidEpistemicDims)
+    l.aid_epistemic_packed_bytes.restype = c_size_t
+    l.aid_epistemic_packed_bytes.argtypes = [D]
+    l.aid_epistemic_pack.restype = c_int32
+    l.aid_epistemic_pack.argtypes = [D, POINTER(c_void_p), c_int32, c_void_p, c_size_t, c_void_p]
+    l.aid_epistemic_workspace_bytes.restype = c_size_t
+    l.aid_epistemic_workspace_bytes.argtypes = [D, c_int32, c_int32]
+    l.aid_epistemic_forward.restype = c_int32
+    l.aid_epistemic_forward.argtypes = [D, c_void_p, c_void_p, c_size_t, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]
+
+
 def _declare_encoder(l: ctypes.CDLL) -> None:
     D = POINTER(AidEncoderDims)
     l.aid_encoder_packed_bytes.restype = c_size_t
@@ -252,6 +271,7 @@ def lib(operand_type: Optional[str] = None) -> ctypes.CDLL:
         _declare_encoder(l)
         _declare_colsum(l)
         _declare_r2(l)
+        _declare_epistemic(l)
         if l.aid_abi_version() != ABI_VERSION:
             raise RuntimeError(f"{path}: ABI version {l.aid_abi_version()} != {ABI_VERSION}; rebuild")
         _libs[name] = l

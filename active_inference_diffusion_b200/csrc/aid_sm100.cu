@@ -1218,6 +1218,7 @@ extern "C" int32_t aid_gemm_nt(const float* a, int64_t a_rs, int64_t a_cs, const
 }
 
 #include "heads.inc"
+#include "epistemic.inc"
 #include "train.inc"
 #include "belief.inc"
 #include "encoder.inc"

@@ -122,6 +122,23 @@ def sharded_mine_statistic(t_joint: torch.Tensor, t_marg: torch.Tensor, group=No
     return (joint - t_exp.log()).float(), joint.float(), t_exp.log().float(), t_exp.float()
 
 
+def merge_mine_partials(partial: torch.Tensor, group=None):
+    """The same statistic from the per-rank partials `aid_epistemic_forward` writes (sum T_joint, max T_marg,
+    sum exp(T_marg - max), N): the sums of exponentials are brought to the global maximum (one MAX
+    all-reduce of a scalar) and then ONE 3-double SUM all-reduce follows.  Returns (mi, joint, log t_exp,
+    t_exp) as 0-dim float tensors."""
+    gmax = partial[1].clone()
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    if multi:
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+    stat = torch.stack([partial[0], partial[2] * torch.exp(partial[1] - gmax), partial[3]])
+    if multi:
+        dist.all_reduce(stat, group=group)
+    joint = stat[0] / stat[2]
+    log_t = gmax + torch.log(stat[1] / stat[2])
+    return (joint - log_t).float(), joint.float(), log_t.float(), torch.exp(log_t).float()
+
+
 def allreduce_grads(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20, group=None) -> None:
     """Average the gradients of `params` over ranks.  Gradients that already live in one contiguous
     buffer (FlatGrads) go out as one collective; others are exchanged tensor by tensor, largest first

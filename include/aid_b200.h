@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AID_ABI_VERSION 2
+#define AID_ABI_VERSION 3
 
 /* LatentScoreNetwork dimensions — models/score_networks.py:20-29 */
 typedef struct AidScoreDims {
@@ -358,6 +358,50 @@ size_t aid_encoder_workspace_bytes(const AidEncoderDims* dims, int32_t batch);
 int32_t aid_encoder_forward(const AidEncoderDims* dims, const void* packed, void* workspace,
                             size_t workspace_bytes, int32_t batch, const void* pixels, int32_t is_u8,
                             float* features, void* stream);
+
+/* ---- function-space epistemic (MINE) estimator, state observations -------------------------------
+ * Replaces FunctionSpaceEpistemicEstimator.forward / compute_jacobian_features
+ * (core/active_inference.py:940-1063) in eval mode (Dropout = identity), with the decoder applied as
+ * decode_observation does (:237-242): observation_decoder = [Linear(L,2H) LN SiLU; Linear(2H,2H) LN
+ * SiLU (+skip); Linear(2H,H) LN SiLU; Linear(H,O)] (:109-131).  Fixed widths of the reference:
+ * feature_extractor O-128-256-128, jacobian_projector 512-512(LN)-J, latent_processor L-128-128,
+ * mine_network (J+128)-512-512-1, ntk_samples 4.
+ * One call: N = num_samples*batch rows; the decoder runs once over 5N stacked rows (base + 4 perturbed),
+ * the feature extractor once over 4N, the MINE network once over 2N (joint | marginal).
+ *   mean, logvar [batch,L]; z_noise [num_samples,batch,L]; dir_noise [4,N,L] (the reference's randn draws,
+ *   in its order); perm_idx [N] int64 = i*batch + randperm_i(batch) (GLOBAL rows of the marginal gather);
+ *   perturbation_scale: device scalar (the module parameter); running_mean: device scalar, updated in
+ *   place by ema_loss's rule (:828-836: first call takes the value, later alpha*t + (1-alpha)*old).
+ *   stats_out [4] (device) = mi, joint term, marginal term, running mean (the reference's four metrics);
+ *   t_out [2N] or NULL = T_joint | T_marg;  partial_out [4] doubles or NULL = sum T_joint,
+ *   max T_marg, sum exp(T_marg - max), N  (what a sharded caller all-reduces). */
+typedef struct AidEpistemicDims {
+  int32_t latent_dim;       /* L, multiple of 8 */
+  int32_t hidden_dim;       /* H of the observation decoder, multiple of 64 */
+  int32_t observation_dim;  /* O */
+  int32_t jacobian_dim;     /* J = spatial_aggregator_output_dim (reference: 256) */
+} AidEpistemicDims;
+enum AidEpistemicParam {   /* W = weight, B = bias, G / BETA = LayerNorm weight / bias */
+  AID_EP_D0_W = 0, AID_EP_D0_B, AID_EP_D0_G, AID_EP_D0_BETA,     /* observation_decoder.0.{0,1} */
+  AID_EP_D1_W, AID_EP_D1_B, AID_EP_D1_G, AID_EP_D1_BETA,         /* observation_decoder.1.{0,1} */
+  AID_EP_D2_W, AID_EP_D2_B, AID_EP_D2_G, AID_EP_D2_BETA,         /* observation_decoder.2.{0,1} */
+  AID_EP_D3_W, AID_EP_D3_B,                                      /* observation_decoder.3 */
+  AID_EP_FE0_W, AID_EP_FE0_B, AID_EP_FE2_W, AID_EP_FE2_B, AID_EP_FE4_W, AID_EP_FE4_B,   /* feature_extractor.{0,2,4} */
+  AID_EP_JP0_W, AID_EP_JP0_B, AID_EP_JP1_G, AID_EP_JP1_BETA, AID_EP_JP4_W, AID_EP_JP4_B, /* jacobian_projector.{0,1,4} */
+  AID_EP_LP0_W, AID_EP_LP0_B, AID_EP_LP2_W, AID_EP_LP2_B,        /* latent_processor.{0,2} */
+  AID_EP_MN0_W, AID_EP_MN0_B, AID_EP_MN3_W, AID_EP_MN3_B, AID_EP_MN6_W, AID_EP_MN6_B,   /* mine_network.{0,3,6} */
+  AID_EP_COUNT
+};
+size_t aid_epistemic_packed_bytes(const AidEpistemicDims* dims);
+int32_t aid_epistemic_pack(const AidEpistemicDims* dims, const float* const* params, int32_t num_params,
+                           void* packed, size_t packed_bytes, void* stream);
+size_t aid_epistemic_workspace_bytes(const AidEpistemicDims* dims, int32_t batch, int32_t num_samples);
+int32_t aid_epistemic_forward(const AidEpistemicDims* dims, const void* packed, void* workspace,
+                              size_t workspace_bytes, int32_t batch, int32_t num_samples,
+                              const float* mean, const float* logvar, const float* z_noise,
+                              const float* dir_noise, const int64_t* perm_idx,
+                              const float* perturbation_scale, float alpha, float* running_mean,
+                              float* stats_out, float* t_out, double* partial_out, void* stream);
 
 /* ---- primitive exposed for tests: y = act(x W^T + b) through the tcgen05 path --------------
  * x [M,K], w [N,K], bias [N] or NULL, y [M,N]; act: 0 none, 1 SiLU, 2 ReLU, 3 GELU(erf).

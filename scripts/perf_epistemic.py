@@ -26,3 +26,12 @@ for epi in (False, True):
         ms = e0.elapsed_time(e1) / 3
         flop = B * K * h * (5781504 + (203.6e6 if epi else 0))
         print(f"EFE B={B} K={K} h={h} epistemic={'on ' if epi else 'off'}: {ms:8.2f} ms  {B / ms * 1e3:10.0f} candidates/s  {flop / ms / 1e9:7.1f} TFLOP/s")
+
+if len(sys.argv) > 2 and sys.argv[2] == "profile":
+    # per-kernel device time of one epistemic-on K=1 call (developer aid)
+    from torch.profiler import profile, ProfilerActivity
+    m.use_epistemic = True
+    with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        m.compute_expected_free_energy_diffusion(lat, horizon=h, num_trajectories=1)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))

@@ -17,6 +17,7 @@ import pytest
 import torch
 
 from oracle import restatement as R
+from oracle.harness import perturb_generic
 from tests.util import gen, make_score_net, rel_l2
 from tests.test_gpu_efe import make_ai
 
@@ -424,7 +425,6 @@ def test_train_epistemic_estimator_step_matches_oracle_gradient():
     With plain SGD (lr 1) the parameter change IS the clipped gradient; compared with autograd on the
     oracle restatement fed the same draws (first call: running mean 0, where the MINE EMA gradient equals
     the plain gradient of log-mean-exp up to its 1e-6 stabiliser)."""
-    from oracle.harness import perturb_generic
     L, A, H, B, S = 32, 6, 128, 48, 3
     ai, nets, cfg = make_ai(L, A, H)
     est = ai.epistemic_estimator
@@ -494,3 +494,78 @@ def test_batched_belief_update_equals_separate_calls():
     assert not torch.equal(infos[1]["latent"], infos[2]["latent"])      # same observations, independent noise rows
     rec = torch.nn.functional.mse_loss(ai.decode_observation(outs[0]), obs)
     assert abs(float(infos[0]["reconstruction_error"]) - float(rec)) < 1e-6 * (1 + float(rec))
+
+
+# ---------------------------------------------------------------------------------------------
+# fused epistemic estimator (csrc/epistemic.inc, aid_epistemic_forward)
+@pytest.mark.parametrize("L,A,H,B,S,fused", [(32, 6, 128, 48, 3, True), (32, 6, 128, 48, 3, False),
+                                             (128, 6, 512, 200, 10, True), (64, 17, 256, 130, 5, True)])
+def test_epistemic_estimator_fused_and_batched_paths_vs_oracle(L, A, H, B, S, fused):
+    """core/active_inference.py:940-1063 (+ decoder shim) with the reference's draws injected: the fused
+    launch sequence on fp16 operands and the batched aid_gemm_nt (bf16x3) evaluation both reproduce the
+    oracle's statistic; two consecutive calls exercise both branches of the running-mean rule (:828-836)."""
+    ai, nets, cfg = make_ai(L, A, H)
+    est = ai.epistemic_estimator
+    est.fused = fused
+    own = {k: v.detach().cpu() for k, v in est.state_dict().items()
+           if not k.startswith("decoder.") and k not in ("perturbation_scale", "running_mean")}
+    est.load_state_dict(perturb_generic(own, 9, 0.05), strict=False)
+    ep = {k: v.detach().cpu().clone() for k, v in est.state_dict().items() if not k.startswith("decoder.")}
+    g = gen(77)
+    rm = 0.0
+    for call in range(2):
+        mean = torch.randn(B, L, generator=g)
+        logvar = torch.full((B, L), float(torch.log(torch.tensor(0.1)))) + 0.1 * torch.randn(B, L, generator=g)
+        z_eps = [torch.randn(B, L, generator=g) for _ in range(S)]
+        dir_eps = [torch.randn(S * B, L, generator=g) for _ in range(4)]
+        perms = [torch.randperm(B, generator=g) for _ in range(S)]
+        with torch.no_grad():
+            want, mi, joint, marg, rm = R.epistemic_value(ep, nets["decoder"], mean, logvar, z_eps, dir_eps, perms, rm)
+            got, stats = est.forward_device(mean.cuda(), logvar.cuda(), S, z_noise=[e.cuda() for e in z_eps],
+                                            dir_noise=[e.cuda() for e in dir_eps], perms=[p.cuda() for p in perms])
+        m = est.metrics_from(stats)
+        assert abs(m["epistemic/joint_term"] - float(joint)) < 1e-3 * (1 + abs(float(joint))), (call, m, float(joint))
+        assert abs(m["epistemic/marginal_term"] - float(marg)) < 1e-3 * (1 + abs(float(marg))), (call, m, float(marg))
+        assert abs(m["epistemic/mi_estimate"] - float(mi)) < 2e-3, (call, m, float(mi))
+        assert torch.allclose(got.cpu(), want, atol=2e-3)
+        assert abs(m["epistemic/running_mean"] - rm) < 1e-3 * (1 + abs(rm)), (call, m, rm)
+        assert abs(float(est.running_mean) - rm) < 1e-3 * (1 + abs(rm))
+
+
+def test_epistemic_fused_sharded_partials_merge_to_global_statistic():
+    """SURVEY 8e row 2 on one process: the per-shard partials of aid_epistemic_forward, merged the way
+    distributed.merge_mine_partials all-reduces them, give the statistic of the unsharded T values."""
+    from active_inference_diffusion_b200 import _lib
+    from active_inference_diffusion_b200.distributed import merge_mine_partials
+    L, A, H, B, S = 32, 6, 128, 64, 3
+    ai, nets, _ = make_ai(L, A, H)
+    est = ai.epistemic_estimator
+    g = gen(5)
+    mean, logvar = torch.randn(B, L, generator=g).cuda(), torch.full((B, L), -2.3).cuda()
+    est.data_parallel_group = None
+    with torch.no_grad():
+        _, stats = est.forward_device(mean, logvar, S)
+    # merging a single shard's partials reproduces that shard's own statistic
+    class _G: pass
+    est.data_parallel_group = torch.distributed.group.WORLD if torch.distributed.is_initialized() else object()
+    est.running_mean.zero_()
+    torch.manual_seed(3)
+    with torch.no_grad():
+        _, s1 = est.forward_device(mean, logvar, S)
+    est.data_parallel_group = None
+    est.running_mean.zero_()
+    torch.manual_seed(3)
+    with torch.no_grad():
+        _, s0 = est.forward_device(mean, logvar, S)
+    assert torch.allclose(s0, s1, atol=1e-6), (s0, s1)
+    # two synthetic shards: partials of halves -> global
+    t = torch.randn(2, 500, dtype=torch.float64, generator=gen(1)).cuda()
+    def part(tj, tm):
+        mx = tm.max()
+        return torch.stack([tj.sum(), mx, torch.exp(tm - mx).sum(), torch.tensor(float(tj.numel()), dtype=torch.float64, device=tj.device)])
+    pa, pb = part(t[0, :200], t[1, :200]), part(t[0, 200:], t[1, 200:])
+    gmax = torch.maximum(pa[1], pb[1])
+    merged = torch.stack([pa[0] + pb[0], gmax, pa[2] * torch.exp(pa[1] - gmax) + pb[2] * torch.exp(pb[1] - gmax), pa[3] + pb[3]])
+    mi, joint, log_t, t_exp = merge_mine_partials(merged)
+    assert abs(float(joint) - float(t[0].mean())) < 1e-6
+    assert abs(float(log_t) - float(t[1].exp().mean().log())) < 1e-6
