@@ -13,8 +13,8 @@ from tests.util import gen, make_score_net, rel_l2
 
 pytestmark = pytest.mark.gpu
 
-SCORE_TOL = 1e-2
-LATENT_TOL = 2e-2
+SCORE_TOL = 1e-2    # measured 5.3e-3 .. 7.9e-3 with the perturbed weights (profiles/r2_measured_errors.txt)
+LATENT_TOL = 6e-3   # measured <= 2.0e-3 on B200 (profiles/r2_measured_errors.txt)
 
 CONFIGS = [  # L, O, H, NB
     (64, 17, 128, 2),
