@@ -93,6 +93,13 @@ def _worker_plumbing(rank, world, port, q):
     gj = torch.Generator().manual_seed(9)
     tj_all, tm_all = torch.randn(world * 40, 1, generator=gj), torch.randn(world * 40, 1, generator=gj)
     mi, joint, marg, t_exp = sharded_mine_statistic(tj_all[rank * 40:(rank + 1) * 40], tm_all[rank * 40:(rank + 1) * 40])
+    # the same statistic from the per-rank partials the fused kernel writes (aid_epistemic_forward):
+    # (sum T_joint, max T_marg, sum exp(T_marg - max), count) -> scalar MAX + 3-double SUM all-reduce
+    from active_inference_diffusion_b200.distributed import merge_mine_partials
+    tj, tm = tj_all[rank * 40:(rank + 1) * 40].double().reshape(-1), tm_all[rank * 40:(rank + 1) * 40].double().reshape(-1)
+    part = torch.stack([tj.sum(), tm.max(), torch.exp(tm - tm.max()).sum(), torch.tensor(40.0, dtype=torch.float64)])
+    mi2, joint2, marg2, _ = merge_mine_partials(part)
+    assert abs(float(mi2) - float(mi)) < 1e-6 and abs(float(joint2) - float(joint)) < 1e-6 and abs(float(marg2) - float(marg)) < 1e-6
     q.put((rank, torch.equal(tg, t_all) and torch.equal(lg, loss_all), w, float(t_mean), fg.flat.clone(),
            (float(mi), float(joint), float(marg))))
     dist.destroy_process_group()
