@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 #           rate: the rel-1e-3 ("fp32/TF32") contract of the sampled latents, EFE, losses, gradients
 LIB_PATHS = {"bf16": os.path.join(_HERE, "libaid_sm100.so"), "f16": os.path.join(_HERE, "libaid_sm100_f16.so")}
 LIB_PATH = LIB_PATHS["bf16"]
-ABI_VERSION = 3
+ABI_VERSION = 4
 OPERAND_TYPES = tuple(LIB_PATHS)
 _operand = os.environ.get("AID_PRECISION", "bf16")
 if _operand not in LIB_PATHS:
@@ -238,6 +238,17 @@ def _declare_epistemic(l: ctypes.CDLL) -> None:
                                         c_void_p]
 
 
+def _declare_conv(l: ctypes.CDLL) -> None:
+    l.aid_conv3x3_workspace_bytes.restype = c_size_t
+    l.aid_conv3x3_workspace_bytes.argtypes = [c_int32] * 7
+    l.aid_conv3x3_forward.restype = c_int32
+    l.aid_conv3x3_forward.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int32] * 7 + [c_void_p, c_void_p, c_size_t, c_void_p]
+    l.aid_conv3x3_wgrad.restype = c_int32
+    l.aid_conv3x3_wgrad.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int32] * 6 + [c_void_p, c_void_p, c_size_t, c_void_p]
+    l.aid_conv3x3_dgrad_direct.restype = c_int32
+    l.aid_conv3x3_dgrad_direct.argtypes = [c_void_p, c_void_p] + [c_int32] * 6 + [c_void_p, c_void_p]
+
+
 def _declare_encoder(l: ctypes.CDLL) -> None:
     D = POINTER(AidEncoderDims)
     l.aid_encoder_packed_bytes.restype = c_size_t
@@ -272,6 +283,7 @@ def lib(operand_type: Optional[str] = None) -> ctypes.CDLL:
         _declare_colsum(l)
         _declare_r2(l)
         _declare_epistemic(l)
+        _declare_conv(l)
         if l.aid_abi_version() != ABI_VERSION:
             raise RuntimeError(f"{path}: ABI version {l.aid_abi_version()} != {ABI_VERSION}; rebuild")
         _libs[name] = l

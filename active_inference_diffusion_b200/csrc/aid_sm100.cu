@@ -1222,6 +1222,7 @@ extern "C" int32_t aid_gemm_nt(const float* a, int64_t a_rs, int64_t a_cs, const
 #include "train.inc"
 #include "belief.inc"
 #include "encoder.inc"
+#include "conv_train.inc"
 
 // ------------------------------------------------------------------------------------------
 extern "C" int32_t aid_abi_version(void) { return AID_ABI_VERSION; }

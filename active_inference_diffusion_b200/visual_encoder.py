@@ -192,20 +192,47 @@ class DrQV2Encoder(nn.Module):
             raise ValueError(f"Expected observations of shape {self.obs_shape}, got {tuple(x.shape[1:])}")
         return x
 
+    # Convolutions of the differentiable graph: "native" = conv_ops.conv3x3 (forward / input gradient /
+    # weight gradient on the library's tcgen05 GEMMs, csrc/conv_train.inc); "torch" = nn.Conv2d (cuDNN),
+    # kept as the cross-check.
+    conv_backend = "native"
+
+    def _conv_weight(self, i: int, x: torch.Tensor) -> torch.Tensor:
+        """The weight nn.Conv2d would use: for a spectral-normed layer the forward pre-hook derives
+        W / sigma from weight_orig (and advances the power iteration in training mode, as the module's
+        own forward does); gradients reach weight_orig through that expression."""
+        conv = self.convs[i]
+        for hook in conv._forward_pre_hooks.values():
+            hook(conv, (x,))
+        return conv.weight
+
     def _forward_autograd(self, x: torch.Tensor) -> torch.Tensor:
         """visual_encoders.py:166-189 as a differentiable graph (training mode / input gradients)."""
-        from . import autograd_path
+        from . import autograd_path, conv_ops
         F = torch.nn.functional
         _lib.require_cuda(x)
         x = x.float() / 255.0 if x.dtype == torch.uint8 else x.float()
+        native = self.conv_backend == "native"
         for i in range(self.num_layers):
-            x = F.mish(self.norms[i](self.convs[i](x)))
+            if native:
+                x = conv_ops.conv3x3(x, self._conv_weight(i, x), 2 if i == 0 else 1, self.precision)
+            else:
+                x = self.convs[i](x)
+            x = F.mish(self.norms[i](x))
             if i + 1 < self.num_layers:
                 x = self.dropouts[i](x)
         if self.use_attention:           # SpatialAttention.forward, :210-224
             att = self.attention
             pooled = torch.cat([x.mean(dim=1, keepdim=True), x.max(dim=1, keepdim=True)[0]], dim=1)
-            x = x + x * torch.sigmoid(att.spatial_conv(pooled) / att.temperature)
+            if native:
+                # the 7x7, 2 -> 1 channel convolution (98 MACs per pixel) as unfold + weighted sum
+                n, _, hh, ww = pooled.shape
+                cols = F.unfold(pooled, kernel_size=7, padding=3)                       # [n, 98, hh*ww]
+                logits = (cols * att.spatial_conv.weight.reshape(1, -1, 1)).sum(dim=1).view(n, 1, hh, ww) \
+                    + att.spatial_conv.bias.view(1, 1, 1, 1)
+            else:
+                logits = att.spatial_conv(pooled)
+            x = x + x * torch.sigmoid(logits / att.temperature)
         x = self.ln(x.reshape(x.shape[0], -1))
         with autograd_path.precision(self.precision):
             return autograd_path.seq(self.output_layers, x)

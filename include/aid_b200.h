@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AID_ABI_VERSION 3
+#define AID_ABI_VERSION 4
 
 /* LatentScoreNetwork dimensions — models/score_networks.py:20-29 */
 typedef struct AidScoreDims {
@@ -402,6 +402,27 @@ int32_t aid_epistemic_forward(const AidEpistemicDims* dims, const void* packed, 
                               const float* dir_noise, const int64_t* perm_idx,
                               const float* perturbation_scale, float alpha, float* running_mean,
                               float* stats_out, float* t_out, double* partial_out, void* stream);
+
+/* ---- 3x3 convolution (padding 1, stride 1 or 2, no bias) for the encoder's TRAINING graph --------
+ * Replaces the nn.Conv2d calls of DrQV2Encoder.forward in training mode and their backward
+ * (encoder/visual_encoders.py:56-76,166-176): forward, input gradient and weight gradient as tcgen05
+ * GEMMs over an explicit im2col operand (k = tap*Cin + c), NCHW fp32 tensors in and out.
+ *   forward : y [n,Cout,Ho,Wo] = conv(x [n,Cin,H,W], w [Cout,Cin,3,3] / *sigma)  (sigma: device scalar or NULL)
+ *   dgrad   : stride 1 = aid_conv3x3_forward(dy, flipped + transposed w); stride 2 = aid_conv3x3_dgrad_direct
+ *   wgrad   : dw [Cout,Cin,3,3] = dy_rows^T * im2col(x) through the MN-major weight-gradient GEMM;
+ *             dy_scale: optional device scalar multiplied into dy before the operand rounding (keeps small
+ *             cotangents inside the fp16 range; the result carries the factor).
+ * precision: 0 = one pass on the library's operand type, 1 = hi/lo split (3x the reduction length). */
+size_t aid_conv3x3_workspace_bytes(int32_t n, int32_t cin, int32_t cout, int32_t H, int32_t W, int32_t stride,
+                                   int32_t precision);
+int32_t aid_conv3x3_forward(const float* x, const float* w, const float* sigma, int32_t n, int32_t cin,
+                            int32_t cout, int32_t H, int32_t W, int32_t stride, int32_t precision, float* y,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int32_t aid_conv3x3_wgrad(const float* x, const float* dy, const float* dy_scale, int32_t n, int32_t cin,
+                          int32_t cout, int32_t H, int32_t W, int32_t stride, float* dw, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int32_t aid_conv3x3_dgrad_direct(const float* dy, const float* w, int32_t n, int32_t cin, int32_t cout,
+                                 int32_t H, int32_t W, int32_t stride, float* dx, void* stream);
 
 /* ---- primitive exposed for tests: y = act(x W^T + b) through the tcgen05 path --------------
  * x [M,K], w [N,K], bias [N] or NULL, y [M,N]; act: 0 none, 1 SiLU, 2 ReLU, 3 GELU(erf).

@@ -191,3 +191,60 @@ def test_encoder_training_mode_and_gradients():
     assert not torch.equal(enc.convs[1].weight_u, u0)                                     # power iteration ran
     a.sum().backward()
     assert enc.output_layers[0].weight.grad is not None
+
+
+# ---------------------------------------------------------------------------------------------
+# training convolutions on the library's GEMMs (csrc/conv_train.inc, conv_ops.py)
+@pytest.mark.parametrize("n,cin,cout,H,W,stride", [(3, 9, 32, 84, 84, 2), (2, 32, 64, 42, 42, 1), (2, 128, 256, 42, 42, 1),
+                                                   (5, 12, 20, 21, 17, 1), (4, 3, 8, 20, 23, 2), (1, 64, 128, 9, 9, 1)])
+@pytest.mark.parametrize("precision", ["bf16x3", "f16"])
+def test_conv3x3_forward_dgrad_wgrad_vs_torch(n, cin, cout, H, W, stride, precision):
+    """nn.Conv2d(k=3, padding=1, bias=False) of encoder/visual_encoders.py:56-76: output, input gradient and
+    weight gradient of conv_ops.conv3x3 against F.conv2d under fp64 autograd."""
+    from active_inference_diffusion_b200 import conv_ops
+    g = gen(n * 1000 + cin)
+    x = torch.randn(n, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)
+    xo, wo = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    want = torch.nn.functional.conv2d(xo, wo, None, stride, 1)
+    dy = torch.randn(want.shape, generator=g) * 1e-4          # small cotangents: the power-of-two scaling matters
+    (want * dy.double()).sum().backward()
+    xg, wg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    got = conv_ops.conv3x3(xg, wg, stride, precision)
+    (got * dy.cuda()).sum().backward()
+    tol_f, tol_g = (2e-5, 1e-3) if precision == "bf16x3" else (1e-3, 1e-3)
+    assert got.shape == want.shape
+    assert rel_l2(got, want) < tol_f, rel_l2(got, want)
+    assert rel_l2(xg.grad, xo.grad) < (1e-5 if stride == 2 else tol_f), rel_l2(xg.grad, xo.grad)   # stride 2: fp32 direct kernel
+    assert rel_l2(wg.grad, wo.grad) < tol_g, rel_l2(wg.grad, wo.grad)
+
+
+def test_encoder_training_graph_contains_no_library_convolution():
+    """With the native convolution backend the training graph (forward + backward) launches no aten
+    convolution op, and its gradients equal those of the cuDNN-backed graph of the same module."""
+    fx = torch.load(os.path.join(GOLD, "encoder_small.pt"), weights_only=False)
+    enc = build(fx["dims"], fx["weights"], "bf16x3")
+    x0 = next(iter(fx["inputs"].values()))
+    x0 = R.encoder_canonical_input(x0, fx["dims"]["obs_shape"][0], fx["dims"]["frame_stack"]).float().cuda()
+    w = None
+    grads = {}
+    for backend in ("native", "torch"):
+        enc.conv_backend = backend
+        enc.zero_grad(set_to_none=True)
+        xg = x0.clone().requires_grad_(True)
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CPU]) as prof:
+            out = enc(xg)
+            w = torch.randn(out.shape, generator=gen(3)).cuda() if w is None else w
+            (out * w).sum().backward()
+        ops = {e.key for e in prof.key_averages()}
+        convs = sorted(o for o in ops if "conv" in o.lower() and o.startswith("aten::"))
+        if backend == "native":
+            assert not convs, convs
+        else:
+            assert convs                                   # the cross-check really runs torch convolutions
+        grads[backend] = {k: p.grad.clone() for k, p in enc.named_parameters() if p.grad is not None}
+        grads[backend]["input"] = xg.grad.clone()
+    assert grads["native"].keys() == grads["torch"].keys()
+    for k in grads["native"]:
+        if float(grads["torch"][k].abs().max()) > 0:
+            assert rel_l2(grads["native"][k], grads["torch"][k]) < 2e-3, (k, rel_l2(grads["native"][k], grads["torch"][k]))

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(operand, code):
     assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), f"{_lib.LIB_PATHS[operand]} does not export {n}"
-    assert lib.aid_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.aid_abi_version() == _lib.ABI_VERSION == 4
     assert lib.aid_operand_type() == code
 
 
