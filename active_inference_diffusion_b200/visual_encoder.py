@@ -225,10 +225,10 @@ class DrQV2Encoder(nn.Module):
             att = self.attention
             pooled = torch.cat([x.mean(dim=1, keepdim=True), x.max(dim=1, keepdim=True)[0]], dim=1)
             if native:
-                # the 7x7, 2 -> 1 channel convolution (98 MACs per pixel) as unfold + weighted sum
-                n, _, hh, ww = pooled.shape
-                cols = F.unfold(pooled, kernel_size=7, padding=3)                       # [n, 98, hh*ww]
-                logits = (cols * att.spatial_conv.weight.reshape(1, -1, 1)).sum(dim=1).view(n, 1, hh, ww) \
+                # the 7x7, 2 -> 1 channel convolution (98 MACs per pixel) as a weighted sum over sliding-window
+                # views of the padded pools (no copy, no library convolution)
+                win = F.pad(pooled, (3, 3, 3, 3)).unfold(2, 7, 1).unfold(3, 7, 1)       # [n, 2, hh, ww, 7, 7]
+                logits = (win * att.spatial_conv.weight.view(1, 2, 1, 1, 7, 7)).sum(dim=(1, 4, 5)).unsqueeze(1) \
                     + att.spatial_conv.bias.view(1, 1, 1, 1)
             else:
                 logits = att.spatial_conv(pooled)
