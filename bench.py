@@ -325,6 +325,30 @@ def bench_train(args, dev, world, rank, barrier):
         loss = float(step.loss)
         out[operand] = {"ms_per_step": float(ms), "samples_per_s": TRAIN_GLOBAL_BATCH / float(ms) * 1e3, "loss": loss}
         del step
+    weak = None
+    if world > 1:
+        # the same step at 32,768 samples PER RANK: what the overlapped gradient all-reduce costs when the
+        # per-rank work does not shrink (the strong-scaling figure above mixes it with small-batch efficiency)
+        Bw = TRAIN_GLOBAL_BATCH
+        gw = torch.Generator().manual_seed(70 + rank)
+        obs_w, rew_w, lat_w = (torch.randn(Bw, L, generator=gw).to(dev), torch.randn(Bw, generator=gw).to(dev),
+                               torch.randn(Bw, L, generator=gw).to(dev))
+        ai.training_path, ai.training_operand = "native", "f16"
+        step = GraphedElboStep(ai, Bw)
+        for _ in range(2):
+            step(obs_w, rew_w, lat_w)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.train_steps):
+            step(obs_w, rew_w, lat_w)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / args.train_steps], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        weak = {"per_rank_batch": Bw, "global_batch": Bw * world, "ms_per_step": float(ms),
+                "samples_per_s": Bw * world / float(ms) * 1e3, "scaling": "weak", "dtype": "f16 operands"}
+        del step
     n_param = sum(p.numel() for p in ai.latent_score_network.parameters()) + sum(p.numel() for p in ai.latent_diffusion.parameters())
     return {
         "workload": "BASELINE configs[2]: score-matching + VFE training step fwd/bwd (+ gradient-penalty double backward), "
@@ -342,6 +366,7 @@ def bench_train(args, dev, world, rank, barrier):
                       "gradients, backward with two input-gradient streams and one merged weight-gradient GEMM per layer); "
                       "autograd on the reference formulation spends 9",
         "loss_f16": out["f16"]["loss"], "loss_bf16": out["bf16"]["loss"],
+        "weak_scaling_32768_per_rank": weak,
     }
 
 
