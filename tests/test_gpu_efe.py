@@ -305,11 +305,12 @@ def test_epistemic_estimator_matches_oracle_with_injected_draws():
     assert abs(metrics["epistemic/running_mean"] - rm) < 1e-3 * (1 + abs(rm))
 
 
-def test_policy_training_gradients_through_efe_rollout():
+@pytest.mark.parametrize("L,A,H,B,K,h", [(32, 6, 128, 40, 2, 3), (128, 6, 512, 300, 2, 5)])
+def test_policy_training_gradients_through_efe_rollout(L, A, H, B, K, h):
     """agents/state_agent.py:162-180: policy_loss = efe.mean(); backward.  When a graph is recorded
     the mirror evaluates the rollout differentiably (every Linear on aid_gemm_nt, bf16x3): efe and
-    the gradients of policy / dynamics / value / reward parameters vs the oracle's autograd."""
-    L, A, H, B, K, h = 32, 6, 128, 40, 2, 3
+    the gradients of policy / dynamics / value / reward parameters vs the oracle's autograd (toy dims
+    and the BASELINE dims L=128 / H=512 at the reference horizon of 5)."""
     ai, nets, cfg = make_ai(L, A, H)
     ai.use_epistemic = False
     g = gen(101)
