@@ -1,6 +1,6 @@
 // Persistent, warp-specialised tcgen05 GEMM with fused epilogues (sm_100a).
 //
-//   D[128 x 128] (TMEM, fp32) = A[128 x K] (bf16, K-major, SW128 tiles) * B[128 x K]^T
+//   D[128 x 128] (TMEM, fp32) = A[128 x K] (16-bit operands, K-major, no-swizzle tiles) * B[128 x K]^T
 //
 // Data layout in HBM (all produced by this library, never by the caller):
 //   * "packed" bf16 operand  : [row_tile][k_block] tiles of R rows x 64 cols (R = 128 for

@@ -194,6 +194,7 @@ __device__ __forceinline__ void tmem_ld_wait() {
 }
 
 // ---------------------------------------------------------------- descriptors
+// (Only scripts/micro/mma_rate.cu uses this one: the layout comparison that decided for no-swizzle tiles.)
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, dense [rows x 64 bf16]
 // tile (row pitch 128 B, 8-row atoms 1024 B apart).  Bit layout (sm_100 "version 1"):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, canonical value 1)
