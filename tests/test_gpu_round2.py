@@ -569,3 +569,39 @@ def test_epistemic_fused_sharded_partials_merge_to_global_statistic():
     mi, joint, log_t, t_exp = merge_mine_partials(merged)
     assert abs(float(joint) - float(t[0].mean())) < 1e-6
     assert abs(float(log_t) - float(t[1].exp().mean().log())) < 1e-6
+
+
+def test_round2_edge_cases_tiny_and_ragged_batches():
+    """Single-row and ragged batches through the round-2 entry points: the fused estimator at B = 1
+    (N = S rows: less than one row tile), the batched belief update over sets of unequal sizes, an empty
+    image batch through the training convolution."""
+    from active_inference_diffusion_b200 import conv_ops, update_belief_batched
+    L, A, H = 32, 6, 128
+    ai, nets, _ = make_ai(L, A, H)
+    est = ai.epistemic_estimator
+    ep = {k: v.detach().cpu().clone() for k, v in est.state_dict().items() if not k.startswith("decoder.")}
+    g = gen(31)
+    for B, S in ((1, 10), (3, 1), (129, 2)):
+        est.running_mean.zero_()
+        mean, logvar = torch.randn(B, L, generator=g), torch.full((B, L), -2.0)
+        z_eps = [torch.randn(B, L, generator=g) for _ in range(S)]
+        dir_eps = [torch.randn(S * B, L, generator=g) for _ in range(4)]
+        perms = [torch.randperm(B, generator=g) for _ in range(S)]
+        with torch.no_grad():
+            want, mi, joint, marg, rm = R.epistemic_value(ep, nets["decoder"], mean, logvar, z_eps, dir_eps, perms, 0.0)
+            got, stats = est.forward_device(mean.cuda(), logvar.cuda(), S, z_noise=[e.cuda() for e in z_eps],
+                                            dir_noise=[e.cuda() for e in dir_eps], perms=[p.cuda() for p in perms])
+        m = est.metrics_from(stats)
+        assert got.shape == (B,)
+        assert abs(m["epistemic/mi_estimate"] - float(mi)) < 2e-3, (B, S, m, float(mi))
+        assert abs(m["epistemic/joint_term"] - float(joint)) < 1e-3 * (1 + abs(float(joint)))
+    d = ai.latent_diffusion
+    d.noise_source = "philox"
+    d.seed_philox(4, torch.device("cuda", 0))
+    sets = [torch.randn(n, L, generator=g).cuda() for n in (1, 130, 7)]
+    infos = update_belief_batched(ai, sets)
+    assert [tuple(i["latent"].shape) for i in infos] == [(1, L), (130, L), (7, L)]
+    assert all(torch.isfinite(i["latent"]).all() for i in infos)
+    assert infos[0]["latent_std"].abs().max() == 0            # single-row set: the reference's batch_size == 1 rule
+    y = conv_ops.conv3x3(torch.zeros(0, 8, 10, 10).cuda(), torch.zeros(16, 8, 3, 3).cuda(), 1, "f16")
+    assert tuple(y.shape) == (0, 16, 10, 10)
