@@ -15,6 +15,12 @@ import torch
 from . import _lib
 
 
+# Images per library call: rows are independent, so larger batches are processed in chunks (forward /
+# input gradient: concatenated; weight gradient: summed) and the workspace stays bounded
+# (512 images of 42x42x256 fp32 rows = 1 GB).
+MAX_IMAGES_PER_CALL = 512
+
+
 def _workspace(l, dev, n, cin, cout, H, W, stride, prec):
     need = l.aid_conv3x3_workspace_bytes(n, cin, cout, H, W, stride, prec)
     if need == 0:
@@ -24,6 +30,8 @@ def _workspace(l, dev, n, cin, cout, H, W, stride, prec):
 
 def conv3x3_forward(x: torch.Tensor, w: torch.Tensor, stride: int = 1, precision: str = "bf16x3") -> torch.Tensor:
     dev = _lib.require_cuda(x, w)
+    if x.shape[0] > MAX_IMAGES_PER_CALL:
+        return torch.cat([conv3x3_forward(c, w, stride, precision) for c in x.split(MAX_IMAGES_PER_CALL)], dim=0)
     op, prec = _lib.PRECISIONS[precision]
     x, w = _lib.f32c(x), _lib.f32c(w)
     n, cin, H, W = x.shape
@@ -50,10 +58,15 @@ def _pow2_scale(t: torch.Tensor) -> torch.Tensor:
 
 def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, stride: int = 1, operand: str = "f16") -> torch.Tensor:
     dev = _lib.require_cuda(x, dy)
+    if x.shape[0] > MAX_IMAGES_PER_CALL:
+        parts = [conv3x3_wgrad(a, b, stride, operand) for a, b in zip(x.split(MAX_IMAGES_PER_CALL), dy.split(MAX_IMAGES_PER_CALL))]
+        return torch.stack(parts).sum(dim=0)
     x, dy = _lib.f32c(x), _lib.f32c(dy)
     n, cin, H, W = x.shape
     cout = dy.shape[1]
     dw = torch.empty(cout, cin, 3, 3, dtype=torch.float32, device=dev)
+    if n == 0:
+        return dw.zero_()
     l = _lib.lib(operand)
     ws = _workspace(l, dev, n, cin, cout, H, W, stride, 0)
     scale = _pow2_scale(dy)
@@ -74,6 +87,8 @@ def conv3x3_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int = 1, p
     dy, w = _lib.f32c(dy), _lib.f32c(w)
     n, cin, H, W = x_shape
     dx = torch.empty(n, cin, H, W, dtype=torch.float32, device=dev)
+    if n == 0:
+        return dx
     l = _lib.lib()
     with torch.cuda.device(dev):
         _lib.check(l.aid_conv3x3_dgrad_direct(dy.data_ptr(), w.data_ptr(), n, cin, w.shape[0], H, W, stride, dx.data_ptr(),

@@ -219,6 +219,24 @@ def test_conv3x3_forward_dgrad_wgrad_vs_torch(n, cin, cout, H, W, stride, precis
     assert rel_l2(wg.grad, wo.grad) < tol_g, rel_l2(wg.grad, wo.grad)
 
 
+def test_conv3x3_chunked_batches_equal_one_call(monkeypatch):
+    """Batches above conv_ops.MAX_IMAGES_PER_CALL are split: same output / gradients as one call."""
+    from active_inference_diffusion_b200 import conv_ops
+    g = gen(77)
+    x, w = torch.randn(7, 8, 12, 12, generator=g).cuda(), (torch.randn(16, 8, 3, 3, generator=g) / 8).cuda()
+    dy = torch.randn(7, 16, 12, 12, generator=g).cuda()
+    outs = []
+    for cap in (512, 3):
+        monkeypatch.setattr(conv_ops, "MAX_IMAGES_PER_CALL", cap)
+        xg, wg = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        y = conv_ops.conv3x3(xg, wg, 1, "f16")
+        (y * dy).sum().backward()
+        outs.append((y.detach(), xg.grad, wg.grad))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert rel_l2(outs[1][1], outs[0][1]) < 1e-3            # the cotangent scale is taken per chunk
+    assert rel_l2(outs[1][2], outs[0][2]) < 1e-3
+
+
 def test_encoder_training_graph_contains_no_library_convolution():
     """With the native convolution backend the training graph (forward + backward) launches no aten
     convolution op, and its gradients equal those of the cuDNN-backed graph of the same module."""
