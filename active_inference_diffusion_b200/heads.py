@@ -227,6 +227,30 @@ class HeadsBundle:
                                                    _lib.stream_ptr(dev)), "aid_head_forward")
         return out
 
+    # Small batches: the K rollouts of a candidate are independent rows, so K*B rows go through ONE
+    # rollout of h steps (18 GEMM launches per step) instead of K sequential ones -- the regime is
+    # launch-latency bound (act(): B = 1, K = 10 in the reference's defaults).  Above this many rows the
+    # kernels are already full and the sequential form keeps the workspace at B rows.
+    TRAJECTORY_ROWS_MAX = 32768
+
+    def _efe_rollout_trajectories_as_rows(self, latent, h, K, cfg, tau, policy_noise, reparam_noise, epistemic):
+        """Same numbers as the K-sequential rollout: a row's arithmetic does not depend on the other rows,
+        and the mean over trajectories is accumulated in the kernel's order (total += G_k / K)."""
+        B, A, L = latent.shape[0], policy_noise.shape[-1], latent.shape[1]
+        rows = latent.repeat(K, 1)                                                      # row k*B + b
+        pn = policy_noise.view(K, h, B, A).permute(1, 0, 2, 3).reshape(h, K * B, A).contiguous()
+        rn = reparam_noise.view(K, h, B, L).permute(1, 0, 2, 3).reshape(h, K * B, L).contiguous()
+        g, first, prag, cons = self.efe_rollout(rows, h, 1, cfg, tau, pn, rn, None)
+        g = g.view(K, B)
+        if epistemic is not None:
+            # batch-constant scalar per (k, t): sum_t gamma^t * epistemic_weight * e[k, t] on top of G_k
+            gam = torch.tensor([cfg["discount_factor"] ** t for t in range(h)], dtype=torch.float32, device=g.device)
+            g = g + (cfg["epistemic_weight"] * (epistemic.view(K, h) * gam).sum(dim=1)).unsqueeze(1)
+        efe = torch.zeros(B, dtype=torch.float32, device=g.device)
+        for k in range(K):
+            efe = efe + g[k] / float(K)
+        return efe, first[:B].contiguous(), prag.view(K, B), cons.view(K, B)
+
     def efe_rollout(self, latent: torch.Tensor, horizon: int, num_trajectories: int, cfg: Dict[str, float],
                     preference_temperature: torch.Tensor, policy_noise: torch.Tensor, reparam_noise: torch.Tensor,
                     epistemic: Optional[torch.Tensor] = None):
@@ -247,6 +271,8 @@ class HeadsBundle:
                                f"(got horizon {h}): use the bf16 operand type for longer horizons")
         assert tuple(policy_noise.shape) == (K * h, B, d.action_dim), policy_noise.shape
         assert tuple(reparam_noise.shape) == (K * h, B, d.latent_dim), reparam_noise.shape
+        if K > 1 and 0 < B * K <= self.TRAJECTORY_ROWS_MAX:
+            return self._efe_rollout_trajectories_as_rows(latent, h, K, cfg, tau, policy_noise, reparam_noise, epistemic)
         efe = torch.empty(B, dtype=torch.float32, device=dev)
         first = torch.empty(B, d.action_dim, dtype=torch.float32, device=dev)
         prag = torch.empty(K, B, dtype=torch.float32, device=dev)

@@ -605,3 +605,30 @@ def test_round2_edge_cases_tiny_and_ragged_batches():
     assert infos[0]["latent_std"].abs().max() == 0            # single-row set: the reference's batch_size == 1 rule
     y = conv_ops.conv3x3(torch.zeros(0, 8, 10, 10).cuda(), torch.zeros(16, 8, 3, 3).cuda(), 1, "f16")
     assert tuple(y.shape) == (0, 16, 10, 10)
+
+
+def test_efe_trajectories_as_rows_equals_sequential_rollouts():
+    """HeadsBundle: K rollouts per candidate evaluated as K*B rows of one rollout (small batches) give
+    bit-identical efe / first action / last-step terms to the K sequential rollouts; with supplied
+    epistemic scalars the two agree to rounding."""
+    L, A, H, B, K, h = 32, 6, 128, 37, 4, 3
+    ai, nets, cfg = make_ai(L, A, H)
+    ai.use_epistemic = False
+    g = gen(12)
+    z = torch.randn(B, L, generator=g).cuda()
+    pn, rn = torch.randn(K * h, B, A, generator=g).cuda(), torch.randn(K * h, B, L, generator=g).cuda()
+    epi = torch.rand(K * h, generator=g).cuda()
+    hb = ai._heads
+    ecfg = dict(epistemic_weight=cfg.epistemic_weight, pragmatic_weight=cfg.pragmatic_weight,
+                consistency_weight=cfg.consistency_weight, discount_factor=cfg.discount_factor)
+    out = {}
+    for mode, cap in (("rows", 32768), ("sequential", 0)):
+        hb.TRAJECTORY_ROWS_MAX = cap
+        with torch.no_grad():
+            out[mode] = hb.efe_rollout(z, h, K, ecfg, ai.preference_temperature, pn, rn, None)
+            out[mode + "_epi"] = hb.efe_rollout(z, h, K, ecfg, ai.preference_temperature, pn, rn, epi)
+    del hb.TRAJECTORY_ROWS_MAX
+    for a, b in zip(out["rows"], out["sequential"]):
+        assert torch.equal(a, b)
+    assert torch.allclose(out["rows_epi"][0], out["sequential_epi"][0], rtol=1e-6, atol=1e-6)
+    assert not torch.equal(out["rows_epi"][0], out["rows"][0])
