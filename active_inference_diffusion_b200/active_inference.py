@@ -496,8 +496,12 @@ class DiffusionActiveInference(nn.Module):
                                             num_samples)
 
     # ---- act (core/active_inference.py:478-531) -------------------------------------------
+    @torch.no_grad()
     def act(self, observation: torch.Tensor, deterministic: bool = False,
             raw_observation: Optional[torch.Tensor] = None):
+        """Runs without recording a graph, as the agents call it (agents/state_agent.py:94-95: under
+        `torch.no_grad()`): belief update, EFE and policy head on the fused kernels; one device->host
+        transfer for every scalar of `info`."""
         observation = observation.to(self.device)
         if observation.dim() == 1:
             observation = observation.unsqueeze(0)

@@ -632,3 +632,43 @@ def test_efe_trajectories_as_rows_equals_sequential_rollouts():
         assert torch.equal(a, b)
     assert torch.allclose(out["rows_epi"][0], out["sequential_epi"][0], rtol=1e-6, atol=1e-6)
     assert not torch.equal(out["rows_epi"][0], out["rows"][0])
+
+
+@pytest.mark.parametrize("use_epistemic", [False, True])
+def test_act_composes_belief_update_efe_and_policy_like_the_reference(use_epistemic):
+    """core/active_inference.py:478-531: act() = update_belief_via_diffusion -> compute_expected_free_energy_
+    diffusion(horizon = config.efe_horizon, K = 10 default) -> policy(latent, deterministic); action on the
+    host with the batch axis squeezed for a single observation; info = belief keys + expected_free_energy,
+    action_log_prob, policy_entropy + the EFE info with every tensor read out as a float.  Replaying the same
+    calls from the same generator state reproduces act()'s numbers (each piece is parity-tested against the
+    oracle on its own)."""
+    L, A, H, T = 32, 6, 128, 6
+    ai, nets, cfg = make_ai(L, A, H, T)
+    ai.use_epistemic = use_epistemic
+    obs = torch.randn(L, generator=gen(2))
+    torch.manual_seed(11)
+    action, info = ai.act(obs, deterministic=True)
+    assert not action.is_cuda and tuple(action.shape) == (A,)
+    for k in ("latent", "latent_mean", "latent_std", "trajectory_length", "reconstruction_error", "observation",
+              "raw_observation", "expected_free_energy", "action_log_prob", "policy_entropy", "epistemic_mean",
+              "pragmatic_mean", "consistency_mean", "num_trajectories", "horizon"):
+        assert k in info, k
+    assert info["horizon"] == cfg.efe_horizon and info["num_trajectories"] == 10
+    assert all(isinstance(info[k], float) for k in ("expected_free_energy", "action_log_prob", "policy_entropy",
+                                                     "epistemic_mean", "pragmatic_mean", "consistency_mean"))
+    if use_epistemic:
+        assert "epistemic/mi_estimate" in info and isinstance(info["epistemic/mi_estimate"], float)
+    # replay
+    ai.epistemic_estimator.running_mean.zero_()
+    torch.manual_seed(11)
+    with torch.no_grad():
+        belief = ai.update_belief_via_diffusion(obs.unsqueeze(0))
+        efe, efe_info = ai.compute_expected_free_energy_diffusion(belief["latent"], horizon=cfg.efe_horizon)
+        act2, logp, dist = ai.policy_network(belief["latent"], deterministic=True)
+    assert torch.equal(info["latent"], belief["latent"])
+    assert abs(info["expected_free_energy"] - float(efe.mean())) <= 1e-6 * (1 + abs(float(efe.mean())))
+    assert torch.equal(action, act2.squeeze(0).cpu())
+    assert abs(info["action_log_prob"] - float(logp.mean())) < 1e-6 * (1 + abs(float(logp.mean())))
+    # batch of observations: action keeps its batch axis
+    a3, _ = ai.act(torch.randn(5, L, generator=gen(3)))
+    assert tuple(a3.shape) == (5, A)
