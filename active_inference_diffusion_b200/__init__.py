@@ -10,11 +10,11 @@ from .active_inference import DiffusionActiveInference
 from .pipeline import CandidateScorer
 from .belief_dynamics import BeliefDynamics, FreeEnergyComputation
 from .visual_encoder import DrQV2Encoder, SpatialAttention
-from .train_utils import RunningMeanStd, update_belief_batched
+from .train_utils import EMAModel, RunningMeanStd, update_belief_batched
 from .train_graph import GraphedElboStep
 
 __all__ = ["ActiveInferenceConfig", "BeliefDynamicsConfig", "DiffusionConfig",
            "LatentDiffusionProcess", "LatentScoreNetwork", "DiffusionConditionedPolicy",
            "LatentDynamicsModel", "ValueNetwork", "DiffusionActiveInference", "CandidateScorer",
            "BeliefDynamics", "FreeEnergyComputation", "DrQV2Encoder", "SpatialAttention", "RunningMeanStd",
-           "update_belief_batched", "GraphedElboStep"]
+           "update_belief_batched", "GraphedElboStep", "EMAModel"]

@@ -220,3 +220,47 @@ def test_device_running_mean_std_matches_reference_normaliser():
         want = torch.tensor(ref.normalize(r.double().numpy()), dtype=torch.float32)
         assert torch.allclose(ours.normalize(r), want, rtol=1e-6, atol=1e-6)
     assert abs(float(ours.mean) - float(ref.mean)) < 1e-12 and abs(float(ours.var) - float(ref.var)) < 1e-12
+
+
+def test_ema_model_matches_reference_arithmetic_and_swaps():
+    """train_utils.EMAModel == core/active_inference.py:779-813 bit for bit over several updates (the
+    reference class itself when the reference tree is importable, its restated formula otherwise);
+    apply_shadow / restore swap param.data and call the module's invalidate_packed."""
+    from active_inference_diffusion_b200.train_utils import EMAModel
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.LayerNorm(5), torch.nn.Linear(5, 3))
+    net[1].bias.requires_grad_(False)                       # frozen parameters are skipped, as in the reference
+    calls = []
+    net.invalidate_packed = lambda: calls.append(1)
+    ours = EMAModel(net, decay=0.99)
+    ref_cls = None
+    try:
+        from oracle import ref_import
+        if ref_import.reference_available():
+            ref_import.import_reference()
+            from active_inference_diffusion.core.active_inference import EMAModel as ref_cls
+    except Exception:
+        ref_cls = None
+    ref = ref_cls(net, decay=0.99) if ref_cls is not None else None
+    want = {n: p.data.clone() for n, p in net.named_parameters() if p.requires_grad}
+    g = torch.Generator().manual_seed(1)
+    for _ in range(4):
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(torch.randn(p.shape, generator=g) * 0.1)
+        ours.update()
+        if ref is not None:
+            ref.update()
+        for n, p in net.named_parameters():
+            if p.requires_grad:
+                want[n] = 0.99 * want[n] + (1 - 0.99) * p.data
+    assert set(ours.shadow) == set(want) and "1.bias" not in ours.shadow
+    for n in want:
+        assert torch.equal(ours.shadow[n], want[n]), n
+        if ref is not None:
+            assert torch.equal(ours.shadow[n], ref.shadow[n]), n
+    before = {n: p.data.clone() for n, p in net.named_parameters()}
+    ours.apply_shadow()
+    assert torch.equal(net[0].weight.data, ours.shadow["0.weight"]) and len(calls) == 1
+    ours.restore()
+    assert all(torch.equal(p.data, before[n]) for n, p in net.named_parameters()) and len(calls) == 2
