@@ -114,6 +114,20 @@ class BeliefDynamics(nn.Module):
         return 0.5 * torch.sum(math.log(2 * math.pi * math.e) + torch.log(torch.clamp(self.variance, min=self.min_eigenvalue)))
 
 
+    def get_diagnostics(self):
+        """core/belief_dynamics.py:391-410, all values from ONE device->host transfer."""
+        if self.config.use_full_covariance:
+            w = torch.linalg.eigvals(self.covariance).real
+            vals = torch.stack([w.min(), w.max(), w.max() / w.min(), torch.det(self.covariance),
+                                self.mean.norm(), self.entropy()]).tolist()
+            keys = ("min_eigenvalue", "max_eigenvalue", "condition_number", "determinant", "mean_norm", "entropy")
+        else:
+            vals = torch.stack([self.variance.min(), self.variance.max(), self.variance.mean(), self.mean.norm(),
+                                self.entropy()]).tolist()
+            keys = ("min_variance", "max_variance", "mean_variance", "mean_norm", "entropy")
+        return dict(zip(keys, vals))
+
+
 class FreeEnergyComputation(nn.Module):
     """F = complexity - accuracy + 0.01 |s_theta|^2 (core/free_energy.py:30-91); the score term runs
     on the sm_100a score forward (no gradient flows through it here)."""

@@ -264,3 +264,21 @@ def test_ema_model_matches_reference_arithmetic_and_swaps():
     assert torch.equal(net[0].weight.data, ours.shadow["0.weight"]) and len(calls) == 1
     ours.restore()
     assert all(torch.equal(p.data, before[n]) for n, p in net.named_parameters()) and len(calls) == 2
+
+
+def test_belief_dynamics_diagnostics_keys_and_values():
+    """core/belief_dynamics.py:391-410: get_diagnostics of the diagonal and the full-covariance belief."""
+    import math
+    from active_inference_diffusion_b200 import BeliefDynamics, BeliefDynamicsConfig
+    for full, keys in ((False, {"min_variance", "max_variance", "mean_variance", "mean_norm", "entropy"}),
+                       (True, {"min_eigenvalue", "max_eigenvalue", "condition_number", "determinant", "mean_norm", "entropy"})):
+        c = BeliefDynamicsConfig()
+        c.use_full_covariance = full
+        b = BeliefDynamics(6, c)
+        b.reset(torch.arange(6.0), torch.diag(torch.tensor([1.0, 2.0, 3.0, 4.0, 5.0, 6.0])))
+        d = b.get_diagnostics()
+        assert set(d) == keys and all(isinstance(v, float) for v in d.values())
+        assert abs(d["mean_norm"] - math.sqrt(55.0)) < 1e-12
+        want_entropy = 0.5 * (6 * math.log(2 * math.pi * math.e) + math.log(720.0))
+        assert abs(d["entropy"] - want_entropy) < 1e-9
+        assert abs(d["min_eigenvalue" if full else "min_variance"] - 1.0) < 1e-9
