@@ -603,6 +603,11 @@ struct ScoreWS {
   __nv_bfloat16 *te_e, *te_h, *ce_a, *ce_b;                    // time-table packed operands
   float4 *tsin, *tcont;                                        // time-table tiled fp32
   float *t_sin_arg, *t_norm, *t_flag, *t_w;                    // time-table per-row scalars
+  // small-batch persistent sampler (small.inc), laid out when batch <= SM_MAX_BATCH
+  float *sm_h0, *sm_h1, *sm_mod, *sm_tsin, *sm_tcont, *sm_obs;
+  __nv_bfloat16 *sm_u, *sm_v;
+  void* sm_steps_raw;
+  unsigned int* sm_bar;
   int* err;
   size_t total;
 };
@@ -635,6 +640,22 @@ static void score_ws_layout(const ScoreW& s, int batch, int table_rows, void* ws
   w.t_norm = a.take<float>((size_t)table_rows * 4);
   w.t_flag = a.take<float>((size_t)table_rows * 4);
   w.t_w = a.take<float>((size_t)table_rows * 4);
+  w.sm_h0 = w.sm_h1 = w.sm_mod = w.sm_tsin = w.sm_tcont = w.sm_obs = nullptr;
+  w.sm_u = w.sm_v = nullptr;
+  w.sm_steps_raw = nullptr;
+  w.sm_bar = nullptr;
+  if (batch <= 256) {   // == SM_MAX_BATCH (small.inc)
+    w.sm_h0 = a.take<float>((size_t)batch * H * 4);
+    w.sm_h1 = a.take<float>((size_t)batch * H * 4);
+    w.sm_mod = a.take<float>((size_t)batch * (2 * s.NB + 1) * 2 * H * 4);
+    w.sm_tsin = a.take<float>((size_t)table_rows * H * 4);
+    w.sm_tcont = a.take<float>((size_t)table_rows * H * 4);
+    w.sm_obs = a.take<float>((size_t)batch * H * 4);
+    w.sm_u = a.take<__nv_bfloat16>((size_t)batch * 4 * H * 2);
+    w.sm_v = a.take<__nv_bfloat16>((size_t)batch * (H / 2) * 2);
+    w.sm_steps_raw = a.take<uint8_t>((size_t)table_rows * 32);
+    w.sm_bar = a.take<unsigned int>(256);
+  }
   w.total = align_up(a.off, 1024);
 }
 
@@ -910,6 +931,8 @@ extern "C" int32_t aid_philox_normal(const void* philox, uint32_t draw, int64_t 
   return 0;
 }
 
+#include "small.inc"
+
 extern "C" int32_t aid_sample_ex(const AidScoreDims* dims, const void* packed, void* workspace,
                                  size_t workspace_bytes, int32_t batch, int32_t n_steps,
                                  const float* step_time_host, const int32_t* step_index_host,
@@ -968,6 +991,9 @@ extern "C" int32_t aid_sample_ex(const AidScoreDims* dims, const void* packed, v
   } else if (traj_out) {
     AID_CHECK(cudaMemcpyAsync(traj_out, z_init, zl * 4, cudaMemcpyDeviceToDevice, st));
   }
+  if (small_path_ok(s, batch))
+    return sample_small(s, w, batch, n_steps, flag, tw, step_index_host, coef_host, T, observation != nullptr,
+                        any_cont, z_init, nz, z_out, traj_out, st);
   const int kbl = ceil_div(s.L, TILE_K);
   k_pack_rows<<<ew_grid((size_t)w.RT * kbl * 1024), 256, 0, st>>>(z_init, batch, s.L, s.L, w.zp, w.RT, kbl, MAP_PLAIN, 0, 1);
   AID_LAUNCH_CHECK("k_pack_rows(z)");
