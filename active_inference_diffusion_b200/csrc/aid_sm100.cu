@@ -654,7 +654,7 @@ static void score_ws_layout(const ScoreW& s, int batch, int table_rows, void* ws
     w.sm_u = a.take<__nv_bfloat16>((size_t)batch * 4 * H * 2);
     w.sm_v = a.take<__nv_bfloat16>((size_t)batch * (H / 2) * 2);
     w.sm_steps_raw = a.take<uint8_t>((size_t)table_rows * 32);
-    w.sm_bar = a.take<unsigned int>(256);
+    w.sm_bar = a.take<unsigned int>(16384);   // barrier counters (SM_BAR_BYTES)
   }
   w.total = align_up(a.off, 1024);
 }

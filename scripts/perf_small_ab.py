@@ -57,7 +57,11 @@ if __name__ == "__main__":
         sys.exit(0)
     batches = sys.argv[1] if len(sys.argv) > 1 else "1,7,32,33,64,256"
     outs = []
-    for tag, env in (("chain", {"AID_SMALL_MAX": "0"}), ("persistent", {})):
+    variants = [("chain", {"AID_SMALL_MAX": "0"}), ("persistent", {})]
+    if os.environ.get("AB_ALL"):
+        variants = [("chain", {"AID_SMALL_MAX": "0"}), ("grid", {"AID_SMALL_CLUSTER": "0"}),
+                    ("cluster8", {"AID_SMALL_CLUSTER": "8"}), ("cluster16", {"AID_SMALL_CLUSTER": "16"})]
+    for tag, env in variants:
         path = f"/tmp/small_ab_{tag}.pt"
         print(f"[{tag}]", flush=True)
         e = dict(os.environ)
@@ -65,11 +69,13 @@ if __name__ == "__main__":
         r = subprocess.run([sys.executable, __file__, "--child", path, batches], env=e, timeout=900)
         if r.returncode != 0:
             print(f"[{tag}] FAILED rc={r.returncode}")
-            sys.exit(1)
+            continue
         outs.append(path)
     import torch
-    a, b = torch.load(outs[0]), torch.load(outs[1])
-    for k in a:
-        d = (a[k] - b[k]).norm() / a[k].norm()
-        print(f"B={k}: rel-L2 persistent vs chain = {float(d):.3e}  max|d| = {float((a[k] - b[k]).abs().max()):.3e}  "
-              f"finite={bool(torch.isfinite(b[k]).all())}")
+    a = torch.load(outs[0])
+    for path in outs[1:]:
+        b = torch.load(path)
+        for k in a:
+            d = (a[k] - b[k]).norm() / a[k].norm()
+            print(f"{os.path.basename(path)} B={k}: rel-L2 vs chain = {float(d):.3e}  max|d| = {float((a[k] - b[k]).abs().max()):.3e}  "
+                  f"finite={bool(torch.isfinite(b[k]).all())}")
