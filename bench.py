@@ -467,8 +467,11 @@ def run_ours(args):
         k10(); ms = timed(k10, 2)
         secondary["num_trajectories_10"] = {"ms_per_step": ms, "value": CANDIDATES / ms * 1e3, "unit": UNIT,
                                             "note": "K=10 rollouts per candidate (the reference default)"}
-        small = {}
-        for b in (1, 256, 4096):
+        # batches <= 256 rows run the reverse diffusion as ONE persistent kernel (csrc/small.inc); 4,096 rows the
+        # tcgen05 launch chain; both replayed as a CUDA graph together with the EFE rollout
+        small = {"note": "scored batch = 50-step reverse diffusion + EFE rollout, one CUDA graph replay; <= 256 rows: "
+                         "persistent small-batch kernel (the launch chain takes 17.2-17.6 ms at these sizes)"}
+        for b in (1, 32, 256, 4096):
             o = obs_dev[:b].contiguous()
             f = lambda: model(o, horizon=HORIZON, num_trajectories=K_TRAJ)
             for _ in range(3):

@@ -138,7 +138,13 @@ int32_t aid_sample(const AidScoreDims* dims, const void* packed, void* workspace
  * of the last GEMM, so no [T-1,B,L] noise tensor exists.  The caller advances the device-side
  * offset between calls (a replayed CUDA graph then draws fresh noise).  deterministic != 0: no
  * per-step noise (core/diffusion.py:233).  The call enqueues only kernels, device-to-device
- * copies and memsets on `stream` (no host-memory copies), so it can be captured in a CUDA graph. */
+ * copies and memsets on `stream` (no host-memory copies), so it can be captured in a CUDA graph.
+ * Batches of at most 256 rows (the sizes of the reference's callers: act() one row, the collector one
+ * row per environment, train_step 256) run all n_steps as ONE persistent kernel (csrc/small.inc: up to 128
+ * co-resident CTAs, grid barrier between layers; needs hidden_dim % 64 == 0 and <= 512, latent_dim % 32
+ * == 0, num_blocks <= 8, otherwise and for larger batches the per-layer tcgen05 launch chain runs).
+ * Same arguments, same noise streams, results equal to the chain's up to 16-bit operand rounding; the
+ * environment variable AID_SMALL_MAX (0..256, read once) moves the switch-over, 0 disables the kernel. */
 typedef struct AidSampleNoise {
   const float* z_init;        /* [B,L] or NULL (requires philox) */
   const float* noise;         /* [n_draws,B,L] or NULL */
