@@ -249,6 +249,44 @@ def test_small_batch_kernel_matches_launch_chain(tmp_path):
         assert rel_l2(drawn, chain[-B]) < LATENT_TOL / 3, (B, rel_l2(drawn, chain[-B]))
 
 
+def test_persistent_samplers_on_two_streams_do_not_deadlock():
+    """The reference's collector samples on its own thread and CUDA stream while the trainer works
+    (utils/async_collector.py:369-451).  The persistent small-batch kernel needs all of its CTAs resident at
+    once (grid barrier); it is launched cooperatively, so two of them issued back to back on two streams run
+    one after the other instead of interleaving CTAs and waiting for each other forever.  Results must equal
+    the serial ones bit for bit."""
+    from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess
+    L, O, H, NB, T = 128, 17, 512, 6, 20
+    net, _ = make_score_net(L, O, H, NB, device="cuda")
+    diff = LatentDiffusionProcess(DiffusionConfig(num_diffusion_steps=T), L).cuda()
+    diff.use_graph = False
+    cases = []
+    for B in (7, 40):
+        g = gen(100 + B)
+        cases.append((B, torch.randn(B, O, generator=g).cuda(), torch.randn(B, L, generator=g).cuda(),
+                      torch.randn(T - 1, B, L, generator=g).cuda()))
+
+    def run(c):
+        B, obs, zT, noise = c
+        return diff.generate_latent_trajectory(net, B, obs, z_init=zT, noise=noise, return_trajectory=False)[-1]
+
+    with torch.no_grad():
+        serial = [run(c).clone() for c in cases]
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        for s in streams:
+            s.wait_stream(torch.cuda.current_stream())
+        outs = [[], []]
+        for _ in range(6):
+            for i, s in enumerate(streams):
+                with torch.cuda.stream(s):
+                    outs[i].append(run(cases[i]).clone())
+        torch.cuda.synchronize()
+    for i in range(2):
+        for o in outs[i]:
+            assert torch.equal(o, serial[i])
+
+
 def test_empty_batch_returns_empty_results():
     """B = 0 (an empty candidate set / replay slice): empty outputs of the right shapes from the score
     forward, the sampler, the heads and the EFE rollout, as the reference's torch modules give."""
