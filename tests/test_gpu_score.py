@@ -190,7 +190,8 @@ def test_alternative_kernel_families_subprocess(env):
     assert out.returncode == 0, out.stderr[-2000:]
 
 
-def test_small_batch_kernel_matches_launch_chain(tmp_path):
+@pytest.mark.parametrize("L,O,H,NB", [(128, 17, 512, 6), (64, 40, 192, 3)])
+def test_small_batch_kernel_matches_launch_chain(tmp_path, L, O, H, NB):
     """Batches of at most 256 rows run the reverse diffusion as ONE persistent kernel (csrc/small.inc:
     128 CTAs split every layer's output columns, grid barrier between layers, mma.sync on the packed
     weights).  It must agree with the tcgen05 launch chain (selected in a child process with
@@ -199,7 +200,7 @@ def test_small_batch_kernel_matches_launch_chain(tmp_path):
     the sampler's bound, with and without a trajectory buffer, and with the Philox stream."""
     import os, subprocess, sys
     from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess
-    L, O, H, NB, T = 128, 17, 512, 6, 6
+    T = 6                        # (64, 40, 192, 3): widths that are not powers of two (3 / 6 / 24 K chunks)
     batches = (1, 17, 33, 200, 256)
     code = ("import sys, torch\n"
             "from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess\n"
