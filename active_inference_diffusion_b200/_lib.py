@@ -236,6 +236,11 @@ def _declare_epistemic(l: ctypes.CDLL) -> None:
     l.aid_epistemic_forward.argtypes = [D, c_void_p, c_void_p, c_size_t, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p]
+    l.aid_epistemic_forward_grouped.restype = c_int32
+    l.aid_epistemic_forward_grouped.argtypes = [D, c_void_p, c_void_p, c_size_t, c_int32, c_int32, c_int32, c_void_p,
+                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    l.aid_ema_sequence.restype = c_int32
+    l.aid_ema_sequence.argtypes = [c_void_p, c_int32, c_float, c_void_p, c_void_p]
 
 
 def _declare_conv(l: ctypes.CDLL) -> None:

@@ -149,19 +149,16 @@ class FunctionSpaceEpistemicEstimator(nn.Module):
     def invalidate_packed(self) -> None:
         self._cache.invalidate()
 
-    def _forward_fused(self, mean, logvar, S, z_noise, dir_noise, perms):
-        """`aid_epistemic_forward`: the whole estimator as one launch sequence on IEEE fp16 tensor-core
-        operands (11-bit significand; fp32 accumulation, LayerNorm, activations and statistic).  The
-        finite differences (f(z + delta) - f(z)) / 0.1 amplify operand rounding ~10x, which is why bf16
-        operands are not offered here: with fp16 the MINE statistic stays within 3e-4 of the fp32
-        oracle at the reference dims (tests/test_gpu_round2.py)."""
+    def _fused_dims(self):
+        L = self.latent_processor[0].in_features
+        H = self.decoder[2][0].out_features
+        return _lib.AidEpistemicDims(L, H, self.decoder[3].out_features, self.jacobian_projector[4].out_features)
+
+    def fused_packed(self, dev: torch.device) -> torch.Tensor:
+        """Packed operand image of the estimator's weights (cached per weight version)."""
         if not hasattr(self, "_cache"):
             object.__setattr__(self, "_cache", _lib.PackedCache())
-        dev = mean.device
-        B, L = mean.shape
-        N = S * B
-        H = self.decoder[2][0].out_features
-        d = _lib.AidEpistemicDims(L, H, self.decoder[3].out_features, self.jacobian_projector[4].out_features)
+        d = self._fused_dims()
         l = _lib.lib(self.FUSED_OPERAND)
         params = self._fused_params()
 
@@ -177,7 +174,20 @@ class FunctionSpaceEpistemicEstimator(nn.Module):
                                                 _lib.stream_ptr(dev)), "aid_epistemic_pack", l)
             return packed
 
-        packed = self._cache.get(("epistemic", self.FUSED_OPERAND), params, build)
+        return self._cache.get(("epistemic", self.FUSED_OPERAND), params, build)
+
+    def _forward_fused(self, mean, logvar, S, z_noise, dir_noise, perms):
+        """`aid_epistemic_forward`: the whole estimator as one launch sequence on IEEE fp16 tensor-core
+        operands (11-bit significand; fp32 accumulation, LayerNorm, activations and statistic).  The
+        finite differences (f(z + delta) - f(z)) / 0.1 amplify operand rounding ~10x, which is why bf16
+        operands are not offered here: with fp16 the MINE statistic stays within 3e-4 of the fp32
+        oracle at the reference dims (tests/test_gpu_round2.py)."""
+        dev = mean.device
+        B, L = mean.shape
+        N = S * B
+        d = self._fused_dims()
+        l = _lib.lib(self.FUSED_OPERAND)
+        packed = self.fused_packed(dev)
         need = l.aid_epistemic_workspace_bytes(ctypes.byref(d), B, S)
         if need == 0:
             _lib.check(-1, "aid_epistemic_workspace_bytes", l)
@@ -209,6 +219,49 @@ class FunctionSpaceEpistemicEstimator(nn.Module):
                                             self.alpha * t_exp + (1.0 - self.alpha) * self.running_mean).reshape(())
             stats = torch.stack([mi.reshape(()), joint.reshape(()), marginal_term.reshape(()), self.running_mean])
         return torch.clamp(stats[0].expand(B), min=0.0), stats
+
+    def forward_grouped(self, mean: torch.Tensor, logvar: torch.Tensor, num_samples: int, groups: int,
+                        *, z_noise=None, dir_noise=None, perms=None) -> torch.Tensor:
+        """`groups` independent estimator evaluations in one launch sequence (`aid_epistemic_forward_grouped`):
+        rows g*Bg .. g*Bg+Bg-1 of `mean` / `logvar` [groups*Bg, L] are the batch of evaluation g.  Returns
+        group_stats [groups, 4] = (mi, joint, marginal term, exp(marginal term)) on the device; the running
+        mean is left to `apply_running_mean` (the reference updates it once per evaluation, in order).
+        Injected draws (tests): z_noise [S, groups*Bg, L], dir_noise [4, S*groups*Bg, L], perms [S, groups, Bg]."""
+        dev = mean.device
+        Bt, L = mean.shape
+        S, Bg = num_samples, Bt // groups
+        N = S * Bt
+        d = self._fused_dims()
+        l = _lib.lib(self.FUSED_OPERAND)
+        packed = self.fused_packed(dev)
+        need = l.aid_epistemic_workspace_bytes(ctypes.byref(d), Bt, S)
+        if need == 0:
+            _lib.check(-1, "aid_epistemic_workspace_bytes", l)
+        ws = self._cache.workspace(need, dev)
+        eps_z = torch.randn(S, Bt, L, device=dev) if z_noise is None else _lib.f32c(z_noise)
+        dirs = torch.randn(self.ntk_samples, N, L, device=dev) if dir_noise is None else _lib.f32c(dir_noise)
+        perm = torch.rand(S, groups, Bg, device=dev).argsort(dim=2) if perms is None else perms.to(dev)
+        # row s*Bt + g*Bg + b of the marginal pass reads row s*Bt + g*Bg + perm[s, g, b]
+        idx = (perm + (torch.arange(S, device=dev).view(S, 1, 1) * Bt
+                       + torch.arange(groups, device=dev).view(1, groups, 1) * Bg)).reshape(-1).contiguous()
+        stats = torch.empty(groups, 4, dtype=torch.float32, device=dev)
+        mean, logvar = _lib.f32c(mean.detach()), _lib.f32c(logvar.detach())
+        eps = self.perturbation_scale.detach().reshape(1).float()
+        with torch.cuda.device(dev):
+            _lib.check(l.aid_epistemic_forward_grouped(
+                ctypes.byref(d), packed.data_ptr(), ws.data_ptr(), ws.numel(), Bt, S, groups, mean.data_ptr(),
+                logvar.data_ptr(), eps_z.data_ptr(), dirs.data_ptr(), idx.data_ptr(), eps.data_ptr(),
+                stats.data_ptr(), _lib.stream_ptr(dev)), "aid_epistemic_forward_grouped", l)
+        return stats
+
+    def apply_running_mean(self, t_exp: torch.Tensor) -> None:
+        """The running-mean updates (:828-836) of the evaluations whose exp(marginal term) are `t_exp`, in order."""
+        t_exp = _lib.f32c(t_exp.reshape(-1))
+        dev = t_exp.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib(self.FUSED_OPERAND).aid_ema_sequence(
+                t_exp.data_ptr(), t_exp.numel(), float(self.alpha), self.running_mean.data.view(1).data_ptr(),
+                _lib.stream_ptr(dev)), "aid_ema_sequence")
 
     METRIC_KEYS = ("epistemic/mi_estimate", "epistemic/joint_term", "epistemic/marginal_term",
                    "epistemic/running_mean")
@@ -413,6 +466,7 @@ class DiffusionActiveInference(nn.Module):
         latent = latent.to(self.device)
         B, K, h = latent.shape[0], num_trajectories, horizon
         dev = latent.device
+        drawn_here = policy_noise is None and reparam_noise is None and epistemic is None
         if policy_noise is None:
             policy_noise = torch.randn(K * h, B, self.action_dim, device=dev)
         if reparam_noise is None:
@@ -422,9 +476,17 @@ class DiffusionActiveInference(nn.Module):
                "consistency_weight": float(self.config.consistency_weight),
                "discount_factor": float(self.config.discount_factor)}
         metrics: Dict[str, float] = {}
+        if drawn_here and self._efe_graph_ok(latent, B):
+            try:
+                return self._efe_graphed(latent, h, K, num_ambiguity_samples, cfg)
+            except RuntimeError as e:          # an operation that cannot be captured on this torch build
+                import warnings
+                warnings.warn(f"EFE CUDA-graph capture failed ({e}); launching directly from now on")
+                self.efe_graph = False
         if epistemic is None and self.use_epistemic:
-            epistemic, metrics = self._epistemic_sequence(latent, h, K, policy_noise, reparam_noise,
-                                                          num_ambiguity_samples)
+            epistemic, stats = self._epistemic_sequence(latent, h, K, policy_noise, reparam_noise,
+                                                        num_ambiguity_samples)
+            metrics = self.epistemic_estimator.metrics_from(stats) if stats is not None else {}
         if any(autograd_path.needs_graph(m, latent) for m in (self.policy_network, self.latent_dynamics,
                                                                self.value_network, self.reward_predictor)):
             # a graph is being recorded (policy training, agents/state_agent.py:165-177): differentiable
@@ -452,6 +514,10 @@ class DiffusionActiveInference(nn.Module):
         vals, stats = [], None
         std = math.exp(0.5 * math.log(0.1))
         A = self.action_dim
+        est = self.epistemic_estimator
+        if (self.epistemic_grouped and K > 1 and latent.is_cuda and est.fused and not est.training
+                and getattr(est, "data_parallel_group", None) is None and latent.shape[0] > 0):
+            return self._epistemic_sequence_grouped(latent, h, K, policy_noise, reparam_noise, num_samples)
         with torch.no_grad():
             for k in range(K):
                 cur = latent
@@ -463,8 +529,108 @@ class DiffusionActiveInference(nn.Module):
                     e, stats = self.epistemic_estimator.forward_device(mean, logvar, num_samples)
                     vals.append(e[0])
                     cur = mean + reparam_noise[d] * std
-        metrics = self.epistemic_estimator.metrics_from(stats) if stats is not None else {}
-        return torch.stack(vals), metrics
+        return torch.stack(vals), stats
+
+    # The K rollouts are independent given the noise: per step t the K estimator evaluations of the reference's
+    # (k, t) loop are ONE grouped launch sequence over K*B rows (h sequences instead of K*h; every evaluation
+    # still sees exactly its own B rows, its own draws and its own permutations), and the running mean is
+    # advanced afterwards through the K*h values in the reference's k-major order.
+    epistemic_grouped = True
+
+    def _epistemic_sequence_grouped(self, latent, h, K, policy_noise, reparam_noise, num_samples):
+        est = self.epistemic_estimator
+        B, A, L = latent.shape[0], self.action_dim, self.latent_dim
+        std = math.exp(0.5 * math.log(0.1))
+        pn = policy_noise.view(K, h, B, A)
+        rn = reparam_noise.view(K, h, B, L)
+        per_step = []
+        with torch.no_grad():
+            cur = latent.repeat(K, 1)                                            # row k*B + b
+            for t in range(h):
+                out = self._heads.head_forward(0, cur)
+                action = out[:, :A] + torch.exp(torch.clamp(out[:, A:], -20, 2)) * pn[:, t].reshape(K * B, A)
+                mean, logvar = self.predict_next_latent(cur, action)
+                per_step.append(est.forward_grouped(mean, logvar, num_samples, K))      # [K, 4]
+                cur = mean + rn[:, t].reshape(K * B, L) * std
+            gs = torch.stack(per_step, dim=1)                                    # [K, h, 4]: (k, t) in k-major order
+            est.apply_running_mean(gs[:, :, 3])
+            vals = torch.clamp(gs[:, :, 0], min=0.0).reshape(K * h)
+            last = gs[K - 1, h - 1]
+            stats = torch.stack([last[0], last[1], last[2], est.running_mean.reshape(())])
+        return vals, stats
+
+    # Small batches -- act() scores ONE observation with K = 10 rollouts x horizon 5 = 50 estimator
+    # evaluations of ~40 launches each, plus the rollout: ~2,300 launches whose issue time (Python + ctypes +
+    # driver, ~14 us each), not their execution, set the latency (32 ms).  Without injected draws and without
+    # autograd recording the whole evaluation is captured once per (batch, K, h, S) and replayed.
+    efe_graph = "auto"
+    efe_graph_max_batch = 256
+
+    def _efe_graph_ok(self, latent: torch.Tensor, B: int) -> bool:
+        if not (self.efe_graph is True or (self.efe_graph == "auto" and 0 < B <= self.efe_graph_max_batch)):
+            return False
+        if not latent.is_cuda or B == 0 or torch.cuda.is_current_stream_capturing():
+            return False
+        if any(autograd_path.needs_graph(m, latent) for m in (self.policy_network, self.latent_dynamics,
+                                                               self.value_network, self.reward_predictor)):
+            return False
+        est = self.epistemic_estimator
+        if self.use_epistemic and not (est.fused and not est.training
+                                       and getattr(est, "data_parallel_group", None) is None):
+            return False          # the unfused / training-mode / sharded estimator rebinds its running mean
+        return True
+
+    def _efe_graphed(self, latent, h, K, S, cfg):
+        dev = latent.device
+        est = self.epistemic_estimator
+        B = latent.shape[0]
+        graphs = self.__dict__.setdefault("_efe_graphs", {})
+        key = (dev, _lib.operand_type(), tuple(latent.shape), h, K, S, bool(self.use_epistemic),
+               tuple(sorted(cfg.items())))
+
+        def guard():
+            # device buffers the captured launches point at: re-packed weights / moved buffers -> capture again
+            return (self._heads.packed_weights().data_ptr(), self.preference_temperature.data_ptr(),
+                    est.running_mean.data_ptr(), est.fused_packed(dev).data_ptr() if self.use_epistemic else 0)
+
+        def body(lat):
+            pn = torch.randn(K * h, B, self.action_dim, device=dev)
+            rn = torch.randn(K * h, B, self.latent_dim, device=dev)
+            epi, stats = (self._epistemic_sequence(lat, h, K, pn, rn, S) if self.use_epistemic else (None, None))
+            efe, first, prag, cons = self._heads.efe_rollout(lat, h, K, cfg, self.preference_temperature, pn, rn, epi)
+            last = epi.view(K, h)[:, -1].clamp(min=0.0).mean() if epi is not None else torch.zeros((), device=dev)
+            return efe, first, prag.mean(), cons.mean(), last, stats
+
+        g = graphs.get(key)
+        if g is not None and g["guard"] != guard():
+            g = None
+        if g is None:
+            g = {"latent": latent.detach().clone()}
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            # the warm-up pass must leave no trace: generator state and the estimator's running mean are put back
+            rng = torch.cuda.get_rng_state(dev)
+            rm = est.running_mean.detach().clone()
+            with torch.cuda.stream(side):
+                body(g["latent"])
+                est.running_mean.data.copy_(rm)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.set_rng_state(rng, dev)
+            g["guard"] = guard()
+            g["graph"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g["graph"]):
+                g["out"] = body(g["latent"])
+            if len(graphs) >= 8:
+                graphs.pop(next(iter(graphs)))
+            graphs[key] = g
+        g["latent"].copy_(latent, non_blocking=True)
+        g["graph"].replay()
+        efe, first, prag, cons, last, stats = g["out"]
+        self.last_first_action = first.clone()
+        metrics = est.metrics_from(stats) if stats is not None else {}
+        info = {"epistemic_mean": last.clone(), "pragmatic_mean": prag.clone(), "consistency_mean": cons.clone(),
+                "num_trajectories": K, "horizon": h, **metrics}
+        return efe.clone(), info
 
     # set by the agent: `agent.active_inference.epistemic_optimizer = Adam(...)` (agents/base_agent.py:134-139)
     epistemic_optimizer = None

@@ -244,7 +244,13 @@ class HeadsBundle:
         g = g.view(K, B)
         if epistemic is not None:
             # batch-constant scalar per (k, t): sum_t gamma^t * epistemic_weight * e[k, t] on top of G_k
-            gam = torch.tensor([cfg["discount_factor"] ** t for t in range(h)], dtype=torch.float32, device=g.device)
+            # (cached per device / discount / horizon: a host->device copy cannot be captured in a CUDA graph)
+            gams = self.__dict__.setdefault("_discount_tables", {})
+            gkey = (g.device, float(cfg["discount_factor"]), h)
+            gam = gams.get(gkey)
+            if gam is None:
+                gam = gams[gkey] = torch.tensor([cfg["discount_factor"] ** t for t in range(h)], dtype=torch.float32,
+                                                device=g.device)
             g = g + (cfg["epistemic_weight"] * (epistemic.view(K, h) * gam).sum(dim=1)).unsqueeze(1)
         efe = torch.zeros(B, dtype=torch.float32, device=g.device)
         for k in range(K):

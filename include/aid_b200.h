@@ -408,6 +408,19 @@ int32_t aid_epistemic_forward(const AidEpistemicDims* dims, const void* packed, 
                               const float* dir_noise, const int64_t* perm_idx,
                               const float* perturbation_scale, float alpha, float* running_mean,
                               float* stats_out, float* t_out, double* partial_out, void* stream);
+/* The same estimator over `groups` independent row sets at once: the K rollouts of one EFE evaluation
+ * (core/active_inference.py:337-378 calls the estimator once per (k, t): 50 calls of ~40 launches for an
+ * act() on one observation; per step t the K calls see independent rows).  batch = groups * Bg rows, group g
+ * = rows g*Bg .. g*Bg+Bg-1 of mean / logvar and of every sample block of z_noise [S, batch, L]; perm_idx must
+ * permute within (sample, group) blocks.  group_stats [groups, 4] = (mi, joint term, marginal term,
+ * exp(marginal term)) per group; the running mean is not touched -- aid_ema_sequence applies the calls'
+ * exp(marginal term) values in the reference's (k, t) order (:828-836). */
+int32_t aid_epistemic_forward_grouped(const AidEpistemicDims* dims, const void* packed, void* workspace,
+                                      size_t workspace_bytes, int32_t batch, int32_t num_samples, int32_t groups,
+                                      const float* mean, const float* logvar, const float* z_noise,
+                                      const float* dir_noise, const int64_t* perm_idx,
+                                      const float* perturbation_scale, float* group_stats, void* stream);
+int32_t aid_ema_sequence(const float* values, int32_t n, float alpha, float* running_mean, void* stream);
 
 /* ---- 3x3 convolution (padding 1, stride 1 or 2, no bias) for the encoder's TRAINING graph --------
  * Replaces the nn.Conv2d calls of DrQV2Encoder.forward in training mode and their backward

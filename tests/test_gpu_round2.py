@@ -499,6 +499,57 @@ def test_batched_belief_update_equals_separate_calls():
     assert abs(float(infos[0]["reconstruction_error"]) - float(rec)) < 1e-6 * (1 + float(rec))
 
 
+def test_grouped_estimator_equals_sequential_evaluations_and_efe_graph_replays():
+    """The EFE loop calls the MINE estimator once per (k, t) (core/active_inference.py:337-378); per step the K
+    calls are independent, so they run as ONE grouped launch sequence (aid_epistemic_forward_grouped) and the
+    running mean is advanced afterwards in the reference's order (aid_ema_sequence).  With the same draws every
+    group's statistic must equal the stand-alone evaluation of its rows, and the running mean the sequential
+    one.  Then: act()-style EFE (no injected draws) replays as a CUDA graph and keeps advancing the running mean."""
+    L, A, H, K, Bg, S = 32, 6, 128, 3, 5, 4
+    ai, _, cfg = make_ai(L, A, H)
+    est = ai.epistemic_estimator
+    assert est.fused and not est.training
+    g = gen(11)
+    Bt, N = K * Bg, S * K * Bg
+    mean = torch.randn(Bt, L, generator=g).cuda()
+    logvar = torch.full((Bt, L), math.log(0.1)).cuda()
+    zn = torch.randn(S, Bt, L, generator=g).cuda()
+    dn = torch.randn(4, N, L, generator=g).cuda()
+    perms = torch.stack([torch.stack([torch.randperm(Bg, generator=g) for _ in range(K)]) for _ in range(S)]).cuda()
+    with torch.no_grad():
+        est.running_mean.zero_()
+        grouped = est.forward_grouped(mean, logvar, S, K, z_noise=zn, dir_noise=dn, perms=perms)
+        assert float(est.running_mean) == 0.0                       # untouched by the grouped call
+        seq = []
+        for k in range(K):
+            rows = slice(k * Bg, (k + 1) * Bg)
+            e, st = est.forward_device(mean[rows], logvar[rows], S, z_noise=[zn[s, rows] for s in range(S)],
+                                       dir_noise=[dn[j].view(S, Bt, L)[:, rows].reshape(S * Bg, L) for j in range(4)],
+                                       perms=[perms[s, k] for s in range(S)])
+            seq.append(st.clone())
+        rm_seq = float(est.running_mean)
+        est.running_mean.zero_()
+        est.apply_running_mean(grouped[:, 3])
+        rm_grouped = float(est.running_mean)
+    for k in range(K):
+        for j in range(3):
+            a, b = float(grouped[k, j]), float(seq[k][j])
+            assert abs(a - b) <= 1e-5 * (1 + abs(b)), (k, j, a, b)
+    assert abs(rm_grouped - rm_seq) <= 1e-6 * (1 + abs(rm_seq)), (rm_grouped, rm_seq)
+    # the whole evaluation as a CUDA graph: two replays draw different noise and advance the running mean twice
+    lat = torch.randn(2, L, generator=g).cuda()
+    with torch.no_grad():
+        est.running_mean.zero_()
+        e1, i1 = ai.compute_expected_free_energy_diffusion(lat, horizon=3, num_trajectories=K, num_ambiguity_samples=S)
+        rm1 = float(est.running_mean)
+        e2, i2 = ai.compute_expected_free_energy_diffusion(lat, horizon=3, num_trajectories=K, num_ambiguity_samples=S)
+        rm2 = float(est.running_mean)
+    assert "_efe_graphs" in ai.__dict__ and len(ai._efe_graphs) == 1 and ai.efe_graph == "auto"
+    assert torch.isfinite(e1).all() and torch.isfinite(e2).all() and not torch.equal(e1, e2)
+    assert rm1 != 0.0 and rm2 != rm1
+    assert abs(i1["epistemic/running_mean"] - rm1) < 1e-6 * (1 + abs(rm1))
+
+
 # ---------------------------------------------------------------------------------------------
 # fused epistemic estimator (csrc/epistemic.inc, aid_epistemic_forward)
 @pytest.mark.parametrize("L,A,H,B,S,fused", [(32, 6, 128, 48, 3, True), (32, 6, 128, 48, 3, False),

@@ -165,17 +165,20 @@ def test_full_size_rows_are_independent_and_shardable():
     assert float(full.std()) > 1e-3
 
 
-@pytest.mark.parametrize("env", [{"AID_CHAIN": "1"}, {"AID_PAIRS": "0"}])
+@pytest.mark.parametrize("env", [{"AID_CHAIN": "1"}, {"AID_PAIRS": "0"}, {"AID_SMALL_CLUSTER": "16"},
+                                 {"AID_SMALL_CLUSTER": "8"}])
 def test_alternative_kernel_families_subprocess(env):
     """The opt-in kernel families (read once per process from the environment): AID_CHAIN=1 = adaLN ->
     next-layer chain kernel (normalised tile handed over in shared memory), AID_PAIRS=0 = single-CTA
-    kernels.  Both must reproduce the oracle's reverse diffusion within the same bound."""
+    kernels, AID_SMALL_CLUSTER=16 / 8 = the persistent small-batch kernel with one thread-block cluster per
+    32-row slab and the hardware cluster barrier instead of the grid barrier (70 rows: three clusters).
+    All must reproduce the oracle's reverse diffusion within the same bound."""
     import os, subprocess, sys
     code = ("import torch\n"
             "from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess\n"
             "from oracle import restatement as R\n"
             "from tests.util import gen, make_score_net, rel_l2\n"
-            "L, O, H, NB, T, B = 128, 17, 512, 6, 4, 300\n"
+            f"L, O, H, NB, T, B = 128, 17, 512, 6, 4, {70 if 'AID_SMALL_CLUSTER' in env else 300}\n"
             "net, params = make_score_net(L, O, H, NB, device='cuda')\n"
             "diff = LatentDiffusionProcess(DiffusionConfig(num_diffusion_steps=T), L).cuda()\n"
             "g = gen(3); obs = torch.randn(B, O, generator=g); zT = torch.randn(B, L, generator=g)\n"
