@@ -316,11 +316,17 @@ __global__ void k_colsum_finish(const float* __restrict__ partial, int parts, in
 }
 
 // =================================================================================================
-// Row kernels.  block = one 128-row tile x RK_CG column groups (thread = (group, row); a warp = 32
-// consecutive rows of one group, so tiled fp32 accesses and packed 16-byte stores are coalesced).
-// A thread walks the 8-column chunks ch = cg, cg + RK_CG, ...  Row reductions go through shared memory.
+// Row kernels.  block = RK_THREADS / CG rows of one 128-row tile x CG column groups (thread = (group, row);
+// a warp = 32 consecutive rows of one group, so tiled fp32 accesses and packed 16-byte stores are coalesced).
+// A thread walks the 8-column chunks ch = cg, cg + CG, ...  Row reductions go through shared memory.
+// CG = 4: a block owns a whole row tile (grid = row tiles; fills the chip from ~150 row tiles on).
+// CG = 16: a block owns 32 rows (grid = 4 x row tiles) -- for the few row tiles of a data-parallel shard
+// (4,096 rows per rank = 32 row tiles: the CG = 4 launches ran on 32 of 148 SMs, 23-36 us each).
 constexpr int RK_CG = 4;
+constexpr int RK_CG_WIDE = 16;
 constexpr int RK_THREADS = RK_CG * TILE_M;
+__host__ __device__ constexpr int rk_rows(int cg) { return RK_THREADS / cg; }
+static inline bool rk_wide(int row_tiles) { return row_tiles < 96; }
 
 struct Tl {            // tiled fp32 tensor view [rt][ld4][128] float4 + float4-column offset
   const float4* p;
@@ -345,19 +351,29 @@ __device__ __forceinline__ void pk_store8(__nv_bfloat16* pk, int kb_total, int k
   *reinterpret_cast<uint4*>(tile + (ch & 7) * (TILE_M * 8) + r * 8) = o;
 }
 // sum of `v` over the RK_CG column groups of row r (all threads of the block call it)
-template <int NV>
-__device__ __forceinline__ void rk_reduce(float (&v)[NV], float* sm /* [NV][RK_CG][128] */, int cg, int r) {
+template <int NV, int CG>
+__device__ __forceinline__ void rk_reduce(float (&v)[NV], float* sm /* [NV][CG][rows of the block] */, int cg, int rl) {
+  constexpr int ROWS = rk_rows(CG);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) sm[(i * RK_CG + cg) * TILE_M + r] = v[i];
+  for (int i = 0; i < NV; ++i) sm[(i * CG + cg) * ROWS + rl] = v[i];
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     float s = 0.f;
 #pragma unroll
-    for (int g = 0; g < RK_CG; ++g) s += sm[(i * RK_CG + g) * TILE_M + r];
+    for (int g = 0; g < CG; ++g) s += sm[(i * CG + g) * ROWS + rl];
     v[i] = s;
   }
   __syncthreads();
+}
+// block -> (row tile, row inside the tile, row inside the block, column group)
+template <int CG>
+__device__ __forceinline__ void rk_coords(int& rt, int& r, int& rl, int& cg) {
+  constexpr int ROWS = rk_rows(CG), SUBS = TILE_M / ROWS;
+  rt = blockIdx.x / SUBS;
+  rl = threadIdx.x % ROWS;
+  r = (blockIdx.x % SUBS) * ROWS + rl;
+  cg = threadIdx.x / ROWS;
 }
 
 // ---- forward: adaLN(h) = LN(h) * (1 + scale) + shift -> packed operand; (mean, rstd) saved --------
@@ -370,8 +386,11 @@ struct AdaLnFwdArgs {
   float2* stat_out;           // [rt*128 + r] (mean, rstd)
   __nv_bfloat16* out_packed;  // [rt][H/64]
 };
+template <int CG>
 __global__ void __launch_bounds__(RK_THREADS) k_adaln_fwd(const AdaLnFwdArgs a) {
-  const int rt = blockIdx.x, r = threadIdx.x & 127, cg = threadIdx.x >> 7;
+  int rt, r, rl, cg;
+  rk_coords<CG>(rt, r, rl, cg);
+  (void)rl;
   float sn = 0.f, mean = 0.f, m2 = 0.f;
   for (int p = 0; p < a.stats_nt; ++p) {
     const float2 s = a.partials[((size_t)rt * a.stats_nt + p) * TILE_M + r];
@@ -380,7 +399,7 @@ __global__ void __launch_bounds__(RK_THREADS) k_adaln_fwd(const AdaLnFwdArgs a) 
   const float rstd = rsqrtf(m2 / (float)a.H + 1e-5f);
   if (cg == 0) a.stat_out[(size_t)rt * TILE_M + r] = make_float2(mean, rstd);
   const int nch = a.H >> 3, kb_total = (a.H + 63) >> 6;
-  for (int ch = cg; ch < nch; ch += RK_CG) {
+  for (int ch = cg; ch < nch; ch += CG) {
     float x[8], sc[8], sh[8], y[8];
     tl_load8(a.h, rt, ch, r, x);
     tl_load8(a.scale, rt, ch, r, sc);
@@ -411,16 +430,18 @@ struct LnBwdArgs {
   Tl s1hat;                   // p == null: none; scaled by s1hat_mul
   float s1hat_mul;
 };
+template <int CG>
 __global__ void __launch_bounds__(RK_THREADS) k_ln_bwd(const LnBwdArgs a) {
-  __shared__ float sm[2 * RK_CG * TILE_M];
-  const int rt = blockIdx.x, r = threadIdx.x & 127, cg = threadIdx.x >> 7;
+  __shared__ float sm[2 * RK_THREADS];
+  int rt, r, rl, cg;
+  rk_coords<CG>(rt, r, rl, cg);
   const int srt = rt % a.src_rt;
   const bool first = rt < a.src_rt;
   const float2 st = a.stat[(size_t)srt * TILE_M + r];
   const float mean = st.x, rstd = st.y;
   const int nch = a.H >> 3, kb_total = (a.H + 63) >> 6;
   float red[2] = {0.f, 0.f};
-  for (int ch = cg; ch < nch; ch += RK_CG) {
+  for (int ch = cg; ch < nch; ch += CG) {
     float av[8], sc[8], x[8];
     tl_load8(a.a, rt, ch, r, av);
     tl_load8(a.scale, srt, ch, r, sc);
@@ -432,10 +453,10 @@ __global__ void __launch_bounds__(RK_THREADS) k_ln_bwd(const LnBwdArgs a) {
       red[1] = fmaf(cn, (x[i] - mean) * rstd, red[1]);
     }
   }
-  rk_reduce<2>(red, sm, cg, r);
+  rk_reduce<2, CG>(red, sm, cg, rl);
   const float inv_h = 1.0f / (float)a.H;
   const float m1 = red[0] * inv_h, m2 = red[1] * inv_h;
-  for (int ch = cg; ch < nch; ch += RK_CG) {
+  for (int ch = cg; ch < nch; ch += CG) {
     float av[8], sc[8], x[8], ci[8], y[8];
     tl_load8(a.a, rt, ch, r, av);
     tl_load8(a.scale, srt, ch, r, sc);
@@ -490,15 +511,17 @@ struct LnHatArgs {
   float4* s1hat;              // tiled [rt][H4][128]
   float4* gp;                 // tiled [rt][H4][128]
 };
+template <int CG>
 __global__ void __launch_bounds__(RK_THREADS) k_ln_hat(const LnHatArgs a) {
-  __shared__ float sm[5 * RK_CG * TILE_M];
-  const int rt = blockIdx.x, r = threadIdx.x & 127, cg = threadIdx.x >> 7;
+  __shared__ float sm[5 * RK_THREADS];
+  int rt, r, rl, cg;
+  rk_coords<CG>(rt, r, rl, cg);
   const float2 st = a.stat[(size_t)rt * TILE_M + r];
   const float mean = st.x, rstd = st.y;
   const float c_mul = __ldg(a.c_mul);
   const int nch = a.H >> 3, kb_total = (a.H + 63) >> 6, H4 = a.a.ld4;
   float red[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // sum a, sum a n, sum c, sum c n, sum a c
-  for (int ch = cg; ch < nch; ch += RK_CG) {
+  for (int ch = cg; ch < nch; ch += CG) {
     float av[8], cv[8], sc[8], x[8];
     tl_load8(a.a, rt, ch, r, av);
     tl_load8(a.ca, rt, ch, r, cv);
@@ -515,14 +538,14 @@ __global__ void __launch_bounds__(RK_THREADS) k_ln_hat(const LnHatArgs a) {
       red[4] = fmaf(av[i], c, red[4]);
     }
   }
-  rk_reduce<5>(red, sm, cg, r);
+  rk_reduce<5, CG>(red, sm, cg, rl);
   const float inv_h = 1.0f / (float)a.H;
   const float m_a = red[0] * inv_h, m_an = red[1] * inv_h, m_c = red[2] * inv_h, m_cn = red[3] * inv_h;
   const float phi0 = red[4] - (float)a.H * (m_a * m_c + m_an * m_cn);
   const float mk = -rstd * (m_a * m_cn + m_c * m_an);       // mean(k)
   const float mkn = -2.0f * rstd * m_an * m_cn;             // mean(k n)
   const float tail = phi0 * rstd * rstd * inv_h;
-  for (int ch = cg; ch < nch; ch += RK_CG) {
+  for (int ch = cg; ch < nch; ch += CG) {
     float av[8], cv[8], sc[8], x[8], o[8], sh[8], g[8];
     tl_load8(a.a, rt, ch, r, av);
     tl_load8(a.ca, rt, ch, r, cv);
