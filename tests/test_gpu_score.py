@@ -253,6 +253,27 @@ def test_small_batch_kernel_matches_launch_chain(tmp_path, L, O, H, NB):
         assert rel_l2(drawn, chain[-B]) < LATENT_TOL / 3, (B, rel_l2(drawn, chain[-B]))
 
 
+@pytest.mark.parametrize("B", [5, 300])
+def test_sampler_without_observation_and_deterministic(B):
+    """`observation=None` (zero observation embedding, models/score_networks.py:146-149) and
+    `deterministic=True` (no per-step noise, core/diffusion.py:233) through both sampler paths: 5 rows = the
+    persistent small-batch kernel, 300 rows = the tcgen05 launch chain."""
+    from active_inference_diffusion_b200 import DiffusionConfig, LatentDiffusionProcess
+    L, O, H, NB, T = 128, 17, 512, 6, 5
+    net, params = make_score_net(L, O, H, NB, device="cuda")
+    diff = LatentDiffusionProcess(DiffusionConfig(num_diffusion_steps=T), L).cuda()
+    g = gen(40 + B)
+    zT = torch.randn(B, L, generator=g)
+    noise = torch.randn(T - 1, B, L, generator=g)
+    with torch.no_grad():
+        want = R.generate_latent_trajectory(params, R.make_schedule(T), zT, None, list(noise))[-1]
+        got = diff.generate_latent_trajectory(net, B, None, z_init=zT.cuda(), noise=noise.cuda())[-1]
+        assert rel_l2(got, want) < LATENT_TOL, rel_l2(got, want)
+        want_d = R.generate_latent_trajectory(params, R.make_schedule(T), zT, None, [], deterministic=True)[-1]
+        got_d = diff.generate_latent_trajectory(net, B, None, deterministic=True, z_init=zT.cuda())[-1]
+        assert rel_l2(got_d, want_d) < LATENT_TOL, rel_l2(got_d, want_d)
+
+
 def test_persistent_samplers_on_two_streams_do_not_deadlock():
     """The reference's collector samples on its own thread and CUDA stream while the trainer works
     (utils/async_collector.py:369-451).  The persistent small-batch kernel needs all of its CTAs resident at
