@@ -593,13 +593,35 @@ class DiffusionActiveInference(nn.Module):
             return (self._heads.packed_weights().data_ptr(), self.preference_temperature.data_ptr(),
                     est.running_mean.data_ptr(), est.fused_packed(dev).data_ptr() if self.use_epistemic else 0)
 
+        gams = self.__dict__.setdefault("_efe_discounts", {})
+
         def body(lat):
             pn = torch.randn(K * h, B, self.action_dim, device=dev)
             rn = torch.randn(K * h, B, self.latent_dim, device=dev)
-            epi, stats = (self._epistemic_sequence(lat, h, K, pn, rn, S) if self.use_epistemic else (None, None))
-            efe, first, prag, cons = self._heads.efe_rollout(lat, h, K, cfg, self.preference_temperature, pn, rn, epi)
-            last = epi.view(K, h)[:, -1].clamp(min=0.0).mean() if epi is not None else torch.zeros((), device=dev)
-            return efe, first, prag.mean(), cons.mean(), last, stats
+            if not self.use_epistemic:
+                efe, first, prag, cons = self._heads.efe_rollout(lat, h, K, cfg, self.preference_temperature, pn, rn, None)
+                return efe, first, prag.mean(), cons.mean(), torch.zeros((), device=dev), None
+            # The estimator sequences and the rollout only meet in the final sum (the epistemic term is one
+            # batch-constant scalar per (k, t): G_k += gamma^t * epistemic_weight * e[k, t], efe = mean_k G_k), so
+            # they run side by side: the estimator on a forked stream (its own workspaces: the caches are keyed by
+            # stream), the rollout here, joined before the scalar is added.
+            gkey = (dev, float(cfg["discount_factor"]), h)
+            if gkey not in gams:                 # first (uncaptured) pass: a host->device copy cannot be captured
+                gams[gkey] = torch.tensor([cfg["discount_factor"] ** t for t in range(h)], dtype=torch.float32, device=dev)
+            main = torch.cuda.current_stream(dev)
+            fork = torch.cuda.Stream(device=dev)
+            fork.wait_stream(main)
+            with torch.cuda.stream(fork):
+                epi, stats = self._epistemic_sequence(lat, h, K, pn, rn, S)
+                term = float(cfg["epistemic_weight"]) * (epi.view(K, h) * gams[gkey]).sum(dim=1).mean()
+                last = epi.view(K, h)[:, -1].clamp(min=0.0).mean()
+            efe, first, prag, cons = self._heads.efe_rollout(lat, h, K, cfg, self.preference_temperature, pn, rn, None)
+            main.wait_stream(fork)
+            for tns in (pn, rn, lat):                 # allocated on `main`, read on `fork`
+                tns.record_stream(fork)
+            for tns in (epi, stats, term, last):      # allocated on `fork`, read on `main`
+                tns.record_stream(main)
+            return efe + term, first, prag.mean(), cons.mean(), last, stats
 
         g = graphs.get(key)
         if g is not None and g["guard"] != guard():
