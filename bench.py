@@ -576,8 +576,26 @@ def epistemic_secondary(dev, timed):
         for _ in range(2):
             f()
         ms = timed(f, 3)
-    return {"candidates": B, "ms_per_call": ms, "value": B / ms * 1e3, "unit": UNIT,
-            "note": "aid_epistemic_forward (fp16 operands) per (k,t); 203.6 MFLOP per candidate-step"}
+    out = {"candidates": B, "ms_per_call": ms, "value": B / ms * 1e3, "unit": UNIT,
+           "note": "aid_epistemic_forward (fp16 operands) per (k,t); 203.6 MFLOP per candidate-step"}
+    # act() as the reference's agents call it once per environment step (core/active_inference.py:478-531): ONE
+    # observation, belief update by 50-step reverse diffusion (persistent kernel), EFE over the default K = 10
+    # rollouts x horizon 5 with the epistemic term on, policy head, one device->host read; wall clock
+    import time
+    ai.latent_score_network.randomize_zero_init(123)
+    obs1 = torch.randn(L)
+    with torch.no_grad():
+        for _ in range(3):
+            ai.act(obs1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            ai.act(obs1)
+        torch.cuda.synchronize()
+    out["act_one_observation"] = {"ms_wall": (time.perf_counter() - t0) / 10 * 1e3, "num_trajectories": 10,
+                                  "horizon": HORIZON, "epistemic": "on",
+                                  "note": "DiffusionActiveInference.act(obs[L]) end to end, host tensor in, action + info dict out"}
+    return out
 
 
 def eager_reference_on_gpu(dev, B):
